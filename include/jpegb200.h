@@ -1,0 +1,244 @@
+/*
+ * jpegb200.h -- C ABI of libjpegb200.so, the B200 (sm_100a) implementation of the
+ * natural_c grayscale JPEG encode hot path.
+ *
+ * Plain C: pointers and sizes only, no torch / CUDA types in any signature (a CUDA
+ * stream is passed as void*).  Three groups of entry points:
+ *
+ *   1. The reference's own core-stage API, same names, same struct layouts, same
+ *      ownership and NULL-on-error behaviour.  A maintainer drops
+ *      natural_c/src/core/ *.c from the build, links -ljpegb200, and
+ *      io/jpeg_handler.c:saveJPEGGrayscale keeps working unmodified.  Host pointers
+ *      in, host pointers out; every stage runs as a CUDA kernel (there is no CPU
+ *      fallback: without a usable GPU every call returns NULL).
+ *   2. The fused entry the shimmed orchestrator calls (BMPImage -> scan bytes in one
+ *      pass over device memory, no per-stage intermediates on the host).
+ *   3. A device-resident encoder handle for batches and for MCU-row stripes of one
+ *      huge image (multi-GPU), used by the bench / Python host layer.
+ *
+ * Reference citations are relative to natural_c/ of
+ * strbac-damjan/jpeg-image-compression.
+ */
+#ifndef JPEGB200_H
+#define JPEGB200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* 1. reference-compatible types (x86-64 layouts verified with sizeof/offsetof) */
+
+#ifndef JPEGB200_NO_REFERENCE_TYPES
+typedef struct BMPImage {            /* include/bmp_handler.h:37-41 (16 B) */
+    int32_t  width;
+    int32_t  height;
+    uint8_t *data;                   /* top-down interleaved RGB, pitch 3*width */
+} BMPImage;
+
+typedef struct {                     /* include/converter.h:21-26 */
+    int      width;                  /* padded to a multiple of 8 */
+    int      height;
+    uint8_t *data;
+} YImage;
+
+typedef struct {                     /* include/converter.h:13-18 */
+    int     width;
+    int     height;
+    int8_t *data;
+} CenteredYImage;
+
+typedef struct {                     /* include/dct.h:14-19 */
+    int    width;
+    int    height;
+    float *coefficients;             /* raster image layout */
+} DCTImage;
+
+typedef struct {                     /* include/quantization.h:10-14 */
+    int      width;
+    int      height;
+    int16_t *data;
+} QuantizedImage;
+
+typedef struct {                     /* include/zigzag.h:7-12 (24 B) */
+    int      numBlocksW;
+    int      numBlocksH;
+    int      totalBlocks;
+    int16_t *data;                   /* [totalBlocks][64] */
+} ZigZagData;
+
+typedef struct {                     /* include/rle.h:8-14 (6 B: u8 @0, u16 @2, u8 @4) */
+    uint8_t  symbol;
+    uint16_t code;
+    uint8_t  codeBits;
+} RLESymbol;
+
+typedef struct {                     /* include/rle.h:17-21 (24 B) */
+    RLESymbol *data;
+    size_t     count;
+    size_t     capacity;
+} RLEData;
+
+typedef struct {                     /* include/huffman.h:9-13 (24 B) */
+    uint8_t *data;
+    size_t   size;
+    size_t   capacity;
+} JpegEncoderBuffer;
+#endif
+
+/* constant tables, value-identical to src/core/jpeg_tables.c:3-48
+ * (declared in include/jpeg_tables.h:7-15) */
+extern const unsigned char std_luminance_quant_tbl[64];
+extern const unsigned char std_dc_luminance_nrcodes[16];
+extern const unsigned char std_dc_luminance_values[12];
+extern const unsigned char std_ac_luminance_nrcodes[16];
+extern const unsigned char std_ac_luminance_values[162];
+
+/* core stages -- each replaces the reference function of the same name.
+ * NULL in (or ->data == NULL) => NULL out; results are malloc'd host structs that
+ * the caller releases with the matching free*. */
+YImage            *convertBMPToJPEGGrayscale(const BMPImage *image);          /* src/core/converter.c:4   (include/converter.h:28) */
+CenteredYImage    *centerYImage(const YImage *source);                        /* src/core/converter.c:60  (include/converter.h:30) */
+void               freeCenteredYImage(CenteredYImage *img);                   /* src/core/converter.c:92  */
+void               computeDCTBlock(const int8_t inputBlock[8][8],
+                                   float outputBlock[8][8]);                  /* src/core/dct.c:63        (include/dct.h:22) */
+DCTImage          *performDCT(const CenteredYImage *image);                   /* src/core/dct.c:98        (include/dct.h:23) */
+void               freeDCTImage(DCTImage *img);                               /* src/core/dct.c:153       */
+QuantizedImage    *quantizeImage(const DCTImage *dctImg);                     /* src/core/quantization.c:3  (include/quantization.h:16) */
+void               freeQuantizedImage(QuantizedImage *img);                   /* src/core/quantization.c:45 */
+ZigZagData        *performZigZag(const QuantizedImage *qImg);                 /* src/core/zigzag.c:21     (include/zigzag.h:14) */
+void               freeZigZagData(ZigZagData *zData);                         /* src/core/zigzag.c:70     */
+RLEData           *performRLE(const ZigZagData *zigZagData);                  /* src/core/rle.c:51        (include/rle.h:23) */
+void               freeRLEData(RLEData *rleData);                             /* src/core/rle.c:129       */
+JpegEncoderBuffer *encodeHuffman(const RLEData *rleData, int totalBlocks);    /* src/core/huffman.c:121   (include/huffman.h:36) */
+void               freeJpegEncoderBuffer(JpegEncoderBuffer *buffer);          /* src/core/huffman.c:195   */
+
+/* host-side I/O kept in C (restated from behaviour, not accelerated) */
+BMPImage *loadBMPImage(const char *filename);                                 /* src/io/bmp_handler.c:15  */
+void      freeBMPImage(BMPImage *image);                                      /* src/io/bmp_handler.c:5   */
+bool      saveJPEGGrayscale(const char *filename, const BMPImage *img);       /* src/io/jpeg_handler.c:119 (fused GPU path inside) */
+void      freeYImage(YImage *img);                                            /* src/io/jpeg_handler.c:284 */
+
+/* ------------------------------------------------------------------------- */
+/* 2. fused entry: everything saveJPEGGrayscale does between fopen and the header
+ *    writes (src/io/jpeg_handler.c:133-201) in one device pass.  Returns the stuffed
+ *    scan bytes (what jpeg_handler.c:252 fwrites), or NULL on any failure. */
+JpegEncoderBuffer *jpegb200_encode_scan(const BMPImage *image);
+
+/* As above, and also returns the first block's 8x8 quantized coefficients in raster
+ * order (the orchestrator prints them, src/io/jpeg_handler.c:168-175). */
+JpegEncoderBuffer *jpegb200_encode_scan_dbg(const BMPImage *image, int16_t first_block[64]);
+
+/* The 328 header bytes of src/io/jpeg_handler.c:220-233 for an image of w x h. */
+size_t jpegb200_jfif_header(int width, int height, uint8_t out[328]);
+
+/* ------------------------------------------------------------------------- */
+/* 3. device-resident encoder */
+
+typedef struct jpegb200_encoder jpegb200_encoder;
+
+enum {
+    JPEGB200_OK = 0,
+    JPEGB200_ERR_CUDA = 1,          /* a CUDA call failed (see jpegb200_last_error) */
+    JPEGB200_ERR_ARG = 2,
+    JPEGB200_ERR_WORKSPACE = 3,     /* packed-bits workspace too small: raise bytes_per_block */
+    JPEGB200_ERR_OUTPUT = 4,        /* caller's scan buffer too small */
+    JPEGB200_ERR_INTERNAL = 5
+};
+
+/* dct_mode: 0 = fast separable DCT + rigorous guard band + exact re-evaluation of
+ * flagged coefficients (default, bit-exact by construction); 1 = every coefficient
+ * in the reference's exact summation order (slow, used to cross-check mode 0). */
+int          jpegb200_device_count(void);
+const char  *jpegb200_last_error(void);
+jpegb200_encoder *jpegb200_encoder_create(int device);
+void         jpegb200_encoder_destroy(jpegb200_encoder *enc);
+int          jpegb200_encoder_set_dct_mode(jpegb200_encoder *enc, int dct_mode);
+int          jpegb200_encoder_set_bytes_per_block(jpegb200_encoder *enc, int bytes_per_block);
+
+/* Description of one launch: `count` images of identical geometry, image i starting
+ * at d_rgb + i*image_stride (top-down interleaved RGB, row pitch 3*width bytes). */
+typedef struct {
+    const uint8_t *d_rgb;
+    int32_t  width;
+    int32_t  height;
+    int32_t  count;
+    uint64_t image_stride;          /* bytes between consecutive images (>= 3*w*h) */
+} jpegb200_batch;
+
+/* Encode a batch resident in device memory.  All arguments are device pointers:
+ *   d_scan          stuffed scan bytes of all images, back to back
+ *   d_scan_offsets  uint64[count+1], byte offset of image i in d_scan ([count] = total)
+ * Asynchronous on `cuda_stream`; call jpegb200_encoder_status after synchronising. */
+int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb200_batch *batch,
+                                 uint8_t *d_scan, uint64_t scan_capacity,
+                                 uint64_t *d_scan_offsets, void *cuda_stream);
+
+/* Device error word of the last launch (0 = ok, else a JPEGB200_ERR_*); synchronises. */
+int jpegb200_encoder_status(jpegb200_encoder *enc, void *cuda_stream);
+
+/* Counters of the last launch (filled after jpegb200_encoder_status). */
+typedef struct {
+    uint64_t blocks;                /* 8x8 blocks processed                           */
+    uint64_t flagged_coefficients;  /* coefficients re-evaluated in reference order    */
+    uint64_t kernel_launches;       /* kernels launched by the last encode call        */
+    uint64_t packed_bytes;          /* unstuffed stream bytes (all images)             */
+} jpegb200_stats;
+int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out);
+
+/* Stage taps for parity tests (device -> host copies; synchronous):
+ * zig-zag coefficients of the last launch widened to int16 [count*blocks][64], and
+ * per-block Huffman bit costs uint32[count*blocks]. */
+int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, uint64_t nblocks);
+int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks);
+
+/* ---- MCU-row stripes of one image across several GPUs ----------------------
+ * Rank r owns block rows [row0, row0+rows) of an image; d_rgb points at the stripe's
+ * first pixel row, stripe_height = pixel rows present in the stripe (the last stripe
+ * carries the image's ragged bottom).  Three phases with two tiny exchanges between
+ * them (done by the caller over NCCL):
+ *
+ *   analyze : block kernel + local bit lengths with DC predictor 0
+ *             -> {first_dc, last_dc, bits_pred0}
+ *   pack    : given the true predictor (previous stripe's last_dc) and the stripe's
+ *             global bit offset, pack at the true global bit phase
+ *             -> {head_byte: bits this stripe contributes to a byte that starts in an
+ *                 earlier stripe, byte_first, byte_last}
+ *   finish  : given the OR of later stripes' head bits for this stripe's last owned
+ *             byte, byte-stuff the owned byte range -> stuffed bytes (device)      */
+typedef struct {
+    int16_t  first_dc;
+    int16_t  last_dc;
+    uint32_t reserved;
+    uint64_t bits_pred0;
+} jpegb200_stripe_summary;
+
+typedef struct {
+    uint64_t bit_begin;             /* global bit offset of the stripe's first bit */
+    uint64_t bit_end;               /* one past its last bit                        */
+    uint32_t head_byte;             /* stripe's contribution to byte bit_begin/8    */
+    uint32_t tail_byte;             /* stripe's contribution to byte (bit_end-1)/8  */
+} jpegb200_stripe_packed;
+
+int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int width,
+                            int stripe_height, jpegb200_stripe_summary *host_out,
+                            void *cuda_stream);
+int jpegb200_stripe_pack(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin,
+                         jpegb200_stripe_packed *host_out, void *cuda_stream);
+int jpegb200_stripe_finish(jpegb200_encoder *enc, uint32_t or_into_last_byte, int owns_first_byte,
+                           int is_last_stripe, uint8_t *d_scan, uint64_t scan_capacity,
+                           uint64_t *host_scan_bytes, void *cuda_stream);
+
+/* Synthetic workload generator on the device:
+ * fills count images of w x h RGB, image i uses seed0 + i. */
+int jpegb200_synth_rgb_device(uint8_t *d_rgb, int width, int height, int count,
+                              uint64_t image_stride, uint32_t seed0, int amp, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEGB200_H */

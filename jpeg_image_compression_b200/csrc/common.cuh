@@ -1,0 +1,115 @@
+// common.cuh -- shared device declarations for libjpegb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jb {
+
+// ---- constant tables (filled once per device by upload_tables; this header is
+// included by exactly one translation unit, jpegb200.cu) -----------------------
+// Reference 6-decimal cosine LUT [spatial][frequency] (natural_c/src/core/dct.c:9-18)
+// and C() factors (dct.c:4-6): used ONLY by the exact (reference-order) evaluation.
+__constant__ float c_ref_cos[64];
+__constant__ float c_ref_scale[64];   // fl(fl(0.25f*C[u])*C[v])            (dct.c:93)
+__constant__ float c_quant_f[64];     // (float)std_luminance_quant_tbl[i]   (quantization.c:35)
+// Fast path: q' = T[u][v] * c_rk[u*8+v], with T the scaled butterfly output.
+__constant__ float c_rk[64];
+__constant__ uint8_t c_zigzag[64];    // raster index of zig-zag position k  (zigzag.c:7-15)
+__constant__ uint8_t c_dc_len[16];    // DC Huffman code length + size, per size class
+__constant__ uint32_t c_dc_code[16];  // (code << 8) | len, per size class
+__constant__ uint32_t c_ac_code[256]; // (code << 8) | len, per (run<<4|size) symbol
+
+// guard-band factor: |s_ref - s_fast| <= kGamma * sum|p| (derivation in DESIGN.md)
+constexpr float kGamma = 1.0e-5f;
+constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: fmaf(x, r, kMagic) rounds x*r to nearest-even integer
+
+// error word bits (device -> host)
+enum : uint32_t {
+    ERRBIT_WORKSPACE = 1u << 0,
+    ERRBIT_OUTPUT = 1u << 1,
+    ERRBIT_LOOKBACK = 1u << 2,
+};
+
+// geometry of one launch: `count` images of w x h, bw x bh blocks each
+struct Geom {
+    const uint8_t *rgb;
+    uint64_t image_stride;
+    int w, h, bw, bh;
+    int spr;                 // 32-block strips per block row
+    int count;
+    uint64_t blocks_per_image;
+    uint64_t total_strips;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// decoupled look-back tile state: [63:42] epoch, [41:40] status, [39:0] value
+constexpr uint64_t LB_VALUE_MASK = (1ull << 40) - 1;
+constexpr int LB_STATUS_SHIFT = 40;
+constexpr int LB_EPOCH_SHIFT = 42;
+constexpr uint32_t LB_AGGREGATE = 1, LB_PREFIX = 2;
+
+__device__ __forceinline__ uint64_t lb_pack(uint32_t epoch, uint32_t status, uint64_t value)
+{
+    return ((uint64_t)epoch << LB_EPOCH_SHIFT) | ((uint64_t)status << LB_STATUS_SHIFT) | (value & LB_VALUE_MASK);
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of the aggregates of tiles [0, tile) of one segment, executed by
+// ONE WARP (all 32 lanes).  `state` points at the segment's tile 0.  Spins are bounded;
+// on timeout sets ERRBIT_LOOKBACK and returns what it has (never hangs the GPU).
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *state, int tile, uint32_t epoch,
+                                                       uint32_t *err)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t excl = 0;
+    int base = tile - 1;
+    while (base >= 0) {
+        const int j = base - lane;
+        uint64_t v = 0;
+        uint32_t status = LB_PREFIX;           // virtual tile before tile 0: prefix 0
+        if (j >= 0) {
+            int spins = 0;
+            for (;;) {
+                v = ld_volatile_u64(state + j);
+                status = (uint32_t)(v >> LB_STATUS_SHIFT) & 3u;
+                if ((uint32_t)(v >> LB_EPOCH_SHIFT) == epoch && status != 0) break;
+                if (++spins > (1 << 22)) { atomicOr(err, ERRBIT_LOOKBACK); status = LB_PREFIX; v = 0; break; }
+                __nanosleep(20);
+            }
+            v &= LB_VALUE_MASK;
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, status == LB_PREFIX);
+        const int first = pmask ? (__ffs(pmask) - 1) : 31;   // nearest tile holding an inclusive prefix
+        uint64_t contrib = (lane <= first) ? v : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (pmask) break;
+        base -= 32;
+    }
+    return excl;
+}
+
+}  // namespace jb

@@ -1,0 +1,324 @@
+// fused_block.cuh -- K1, the fused block kernel.
+//
+// One pass over the RGB payload: luma (converter.c:51) + edge replication
+// (converter.c:31,36) + level shift (converter.c:84-86) + 8x8 forward DCT (dct.c:63-96)
+// + quantization (quantization.c:34-36) + zig-zag (zigzag.c:51-60) + the AC part of the
+// block's Huffman bit cost (rle.c:83-123 with huffman.c code lengths).
+//
+// Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels,
+// 6 KB of RGB).  One warp owns a strip:
+//   1. 16-byte cp.async (LDGSTS, L2-only) of the 8 pixel rows into shared memory, at
+//      the rows' natural 16-byte phase (any width / base alignment: one generic path);
+//   2. cooperative luma pass: 4 pixels per lane-step (funnel-shift realign, PRMT, DP4A),
+//      bytes written to a 256 x 8 Y tile;
+//   3. the next strip's cp.async is issued (the raw tile is free again) so its HBM
+//      latency overlaps the arithmetic below;
+//   4. one lane per 8x8 block, block entirely in registers: magic-number u8->f32,
+//      scaled even/odd butterfly DCT (rows then columns), quantization by one FFMA per
+//      bound (see below), zig-zag packing to int8 with PRMT, AC bit cost by table
+//      look-up, 4 x 128-bit stores of the 64 coefficients.
+//
+// Bit-exactness.  The reference sums 64 products sequentially in fp32 with two unfused
+// multiplies per term; replaying that costs ~136 flop/pixel.  Instead the butterfly
+// value T (ideal cosines, FMA) is bracketed: the reference's sum s_ref satisfies
+// |s_ref - g*T| <= kGamma * A with A = sum|p| over the block (DESIGN.md derives the
+// bound: 66u*A for the reference's own roundings, 24u*A for the butterfly's, 1.45e-6*A
+// for the 6-decimal LUT vs ideal cosines, 2^-20*A for the scale/divide roundings;
+// u = 2^-24).  Quantization is monotone in s, so if rounding (T-E)*rk and (T+E)*rk give
+// the same integer that integer IS the reference's; otherwise (about 1e-4 of the
+// coefficients) the lane re-evaluates that one coefficient in the reference's exact
+// operation order (exact_quantized below).  The DC term is an exact integer sum in both
+// formulations and is quantized with the reference's own operation sequence.
+#pragma once
+
+#include "common.cuh"
+
+namespace jb {
+
+constexpr int K1_WARPS = 8;
+constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr int RAW_PITCH = 784;                       // 768 payload + 16 bytes of alignment slack
+constexpr int RAW_BYTES = 8 * RAW_PITCH;             // 6272
+constexpr int Y_PITCH = 256;
+constexpr int Y_BYTES = 8 * Y_PITCH;                 // 2048
+constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES;    // 8320
+constexpr int ACLUT_ROWS = 63;                       // run 0..62
+constexpr int ACLUT_BYTES = 16384;                   // 63*256 rounded up
+constexpr int K1_SMEM = ACLUT_BYTES + K1_WARPS * K1_WARP_SMEM;   // 82944
+
+struct StripPos {
+    uint64_t img;
+    int brow, sx;
+};
+
+__device__ __forceinline__ StripPos strip_pos(const Geom &g, uint64_t s)
+{
+    const uint64_t per_image = (uint64_t)g.bh * (uint64_t)g.spr;
+    StripPos p;
+    p.img = s / per_image;
+    const uint32_t rem = (uint32_t)(s - p.img * per_image);
+    p.brow = (int)(rem / (uint32_t)g.spr);
+    p.sx = (int)(rem - (uint32_t)p.brow * (uint32_t)g.spr);
+    return p;
+}
+
+__device__ __forceinline__ const uint8_t *strip_row_ptr(const Geom &g, const StripPos &p, int r)
+{
+    int y = p.brow * 8 + r;
+    y = y < g.h ? y : g.h - 1;                                            // converter.c:31
+    return g.rgb + p.img * g.image_stride + ((uint64_t)y * (uint64_t)g.w + (uint64_t)p.sx * 256u) * 3u;
+}
+
+// stage the strip's 8 pixel rows (cp.async, 16 B per lane-step)
+__device__ __forceinline__ void strip_issue_loads(const Geom &g, uint64_t s, uint8_t *raw, int lane)
+{
+    const StripPos p = strip_pos(g, s);
+    const int npx = min(256, g.w - p.sx * 256);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint8_t *src = strip_row_ptr(g, p, r);
+        const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
+        const uint8_t *a0 = src - mis;
+        const int nch = (int)((mis + 3u * (uint32_t)npx + 15u) >> 4);
+        for (int c = lane; c < nch; c += 32) cp_async16(raw + r * RAW_PITCH + c * 16, a0 + c * 16);
+    }
+    cp_async_commit();
+}
+
+// Reference-order evaluation of ONE quantized coefficient (dct.c:65-93,
+// quantization.c:34-36): sequential fp32 sum, two unfused multiplies per term, IEEE
+// divide, round half away from zero.  yblk: the block's Y bytes (pitch Y_PITCH).
+__device__ __noinline__ int exact_quantized(const uint8_t *yblk, int u, int v)
+{
+    float acc = 0.0f;
+    for (int r = 0; r < 8; ++r) {
+        const float cu = c_ref_cos[r * 8 + u];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float pix = (float)((int)yblk[r * Y_PITCH + c] - 128);   // converter.c:84
+            float t = __fmul_rn(pix, cu);
+            t = __fmul_rn(t, c_ref_cos[c * 8 + v]);
+            acc = __fadd_rn(acc, t);
+        }
+    }
+    const float f = __fmul_rn(c_ref_scale[u * 8 + v], acc);
+    return (int)roundf(__fdiv_rn(f, c_quant_f[u * 8 + v]));
+}
+
+// Scaled 8-point DCT-II butterfly.  Outputs T_k = S_k / g_k with S_k = sum x_i cos((2i+1)k pi/16),
+// g = {1,1,cos(pi/8),1,cos(pi/4),1,cos(pi/8),1}; the g factors are folded into c_rk.
+__device__ __forceinline__ void dct8(float &x0, float &x1, float &x2, float &x3, float &x4, float &x5,
+                                     float &x6, float &x7)
+{
+    constexpr float C1 = 0.98078528040323044913f, C3 = 0.83146961230254523708f;
+    constexpr float C5 = 0.55557023301960222474f, C7 = 0.19509032201612826785f;
+    constexpr float TAN = 0.41421356237309504880f;              // tan(pi/8)
+    const float a0 = x0 + x7, a1 = x1 + x6, a2 = x2 + x5, a3 = x3 + x4;
+    const float b0 = x0 - x7, b1 = x1 - x6, b2 = x2 - x5, b3 = x3 - x4;
+    const float e0 = a0 + a3, e1 = a1 + a2, d0 = a0 - a3, d1 = a1 - a2;
+    x0 = e0 + e1;
+    x4 = e0 - e1;
+    x2 = fmaf(d1, TAN, d0);
+    x6 = fmaf(d0, TAN, -d1);
+    x1 = fmaf(b3, C7, fmaf(b2, C5, fmaf(b1, C3, b0 * C1)));
+    x3 = fmaf(b3, -C5, fmaf(b2, -C1, fmaf(b1, -C7, b0 * C3)));
+    x5 = fmaf(b3, C3, fmaf(b2, C7, fmaf(b1, -C1, b0 * C5)));
+    x7 = fmaf(b3, -C1, fmaf(b2, C3, fmaf(b1, -C5, b0 * C7)));
+}
+
+// scale class of a frequency index: 0 -> g=1, 1 -> g=cos(pi/8), 2 -> g=cos(pi/4)
+__host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 : (k == 4 ? 2 : 0); }
+
+__device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
+{
+    // 0x4B0000xx is 2^23 + xx; subtracting 2^23 + 128 is exact.
+    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)byte);
+    return __uint_as_float(bits) - 8388736.0f;
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 2)
+k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blockinfo,
+               const uint8_t *__restrict__ aclut_g, unsigned long long *__restrict__ flagged_counter,
+               const int exact_mode)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *aclut = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *raw = smem + ACLUT_BYTES + warp * K1_WARP_SMEM;
+    uint8_t *ybuf = raw + RAW_BYTES;
+
+    for (int i = threadIdx.x; i < ACLUT_BYTES / 16; i += K1_THREADS)
+        reinterpret_cast<uint4 *>(aclut)[i] = reinterpret_cast<const uint4 *>(aclut_g)[i];
+    __syncthreads();
+
+    const uint64_t nwarps = (uint64_t)gridDim.x * K1_WARPS;
+    uint64_t s = (uint64_t)blockIdx.x * K1_WARPS + warp;
+    if (s < g.total_strips) strip_issue_loads(g, s, raw, lane);
+    uint32_t nflag = 0;
+
+    for (; s < g.total_strips; s += nwarps) {
+        const StripPos p = strip_pos(g, s);
+        const int npx = min(256, g.w - p.sx * 256);               // real pixels in the strip
+        const int vb = min(32, g.bw - p.sx * 32);                 // blocks in the strip
+        uint32_t mispack = 0;                                     // 16-byte phase of each row
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            mispack |= (uint32_t)((uintptr_t)strip_row_ptr(g, p, r) & 15u) << (4 * r);
+
+        cp_async_wait_all();
+        __syncwarp();
+
+        // ---- luma pass: Y = (77R + 150G + 29B) >> 8  (converter.c:51) --------------
+        const int ngroups = (npx + 3) >> 2;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int item = lane + 32 * i;
+            const int r = item >> 6, gc = item & 63;
+            if (gc < ngroups) {
+                const uint32_t mis = (mispack >> (4 * r)) & 15u;
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH) + (mis >> 2) + 3 * gc;
+                const uint32_t sh = (mis & 3u) * 8u;
+                const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
+                const uint32_t w0 = __funnelshift_r(q0, q1, sh);
+                const uint32_t w1 = __funnelshift_r(q1, q2, sh);
+                const uint32_t w2 = __funnelshift_r(q2, q3, sh);
+                const uint32_t y0 = __dp4a(w0, 0x001D964Du, 0u);
+                const uint32_t y1 = __dp4a(__byte_perm(w0, w1, 0x0543u), 0x001D964Du, 0u);
+                const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), 0x001D964Du, 0u);
+                const uint32_t y3 = __dp4a(w2, 0x1D964D00u, 0u);
+                const uint32_t lo = __byte_perm(y0, y1, 0x0051u), hi = __byte_perm(y2, y3, 0x0051u);
+                reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] = __byte_perm(lo, hi, 0x5410u);
+            }
+        }
+        __syncwarp();
+
+        // raw tile is free: prefetch the next strip while this one is transformed
+        if (s + nwarps < g.total_strips) strip_issue_loads(g, s + nwarps, raw, lane);
+
+        // right-edge replication inside the last real block (converter.c:36)
+        const int padpx = vb * 8 - npx;
+        if (padpx > 0) {
+            if (lane < padpx) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) ybuf[r * Y_PITCH + npx + lane] = ybuf[r * Y_PITCH + npx - 1];
+            }
+            __syncwarp();
+        }
+
+        if (lane < vb) {
+            const uint8_t *yblk = ybuf + lane * 8;
+            float x[8][8];
+            uint32_t absdev = 0;                                   // A = sum |Y - 128|
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
+                absdev = __vsadu4(v.x, 0x80808080u) + absdev;
+                absdev = __vsadu4(v.y, 0x80808080u) + absdev;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    x[r][c] = u8_to_centered(v.x, c);
+                    x[r][c + 4] = u8_to_centered(v.y, c);
+                }
+                dct8(x[r][0], x[r][1], x[r][2], x[r][3], x[r][4], x[r][5], x[r][6], x[r][7]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                dct8(x[0][c], x[1][c], x[2][c], x[3][c], x[4][c], x[5][c], x[6][c], x[7][c]);
+
+            // guard half-widths in T units for the 6 scale-class pairs
+            const float eb = (float)absdev * kGamma;
+            float ecls[3][3];
+            {
+                constexpr float IG[3] = {1.0f, 1.0823922002923940f, 1.4142135623730951f};   // 1/g, rounded up
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) ecls[a][b] = eb * (IG[a] * IG[b] * 1.000001f);
+            }
+
+            // quantize in zig-zag order, pack to int8 (low byte of the magic-biased float)
+            uint32_t zw[16], xw[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                uint32_t hb[4], lb[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    constexpr uint8_t ZZ[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                                12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                                35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                                58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+                    const int pos = ZZ[4 * w + j], u = pos >> 3, v = pos & 7;
+                    const float t = x[u][v];
+                    const float e = ecls[gclass(u)][gclass(v)];
+                    const float rk = c_rk[pos];
+                    hb[j] = __float_as_uint(fmaf(__fadd_rn(t, e), rk, kMagic));
+                    lb[j] = __float_as_uint(fmaf(__fadd_rn(t, -e), rk, kMagic));
+                }
+                const uint32_t h = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040u), __byte_perm(hb[2], hb[3], 0x0040u), 0x5410u);
+                const uint32_t l = __byte_perm(__byte_perm(lb[0], lb[1], 0x0040u), __byte_perm(lb[2], lb[3], 0x0040u), 0x5410u);
+                zw[w] = h;
+                xw[w] = exact_mode ? 0x01010101u : (h ^ l);
+            }
+
+            // DC: exact integer sum in both formulations; reference operation sequence
+            // fl(k00 * S) / 16 then roundf (dct.c:93, quantization.c:36)
+            {
+                const float f = __fmul_rn(c_ref_scale[0], x[0][0]);
+                const int dcq = (int)roundf(f * 0.0625f);
+                zw[0] = (zw[0] & 0xFFFFFF00u) | ((uint32_t)dcq & 0xFFu);
+                xw[0] &= 0xFFFFFF00u;
+            }
+
+            uint32_t anyx = 0;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) anyx |= xw[w];
+            if (anyx) {                                            // rare: reference-order re-evaluation
+#pragma unroll
+                for (int w = 0; w < 16; ++w) {
+                    if (xw[w]) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if ((xw[w] >> (8 * j)) & 0xFFu) {
+                                const int pos = c_zigzag[4 * w + j];
+                                const int q = exact_quantized(yblk, pos >> 3, pos & 7);
+                                zw[w] = (zw[w] & ~(0xFFu << (8 * j))) | (((uint32_t)q & 0xFFu) << (8 * j));
+                                ++nflag;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // AC bit cost: code length + amplitude bits per non-zero coefficient, ZRLs, EOB
+            uint32_t bits = 0, lastk256 = 0;
+#pragma unroll
+            for (int k = 1; k < 64; ++k) {
+                const uint32_t byte = __byte_perm(zw[k >> 2], 0u, 0x4440u + (uint32_t)(k & 3));
+                bits += aclut[byte + (uint32_t)((k - 1) * 256) - lastk256];
+                if (byte != 0) lastk256 = (uint32_t)(k * 256);
+            }
+            if (lastk256 != 63u * 256u) bits += (c_ac_code[0] & 0xFFu);   // EOB (rle.c:121-123)
+
+            const uint64_t b = p.img * g.blocks_per_image + (uint64_t)p.brow * (uint64_t)g.bw + (uint64_t)(p.sx * 32 + lane);
+            uint4 *dst = reinterpret_cast<uint4 *>(coef + b * 64);
+            dst[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+            dst[1] = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+            dst[2] = make_uint4(zw[8], zw[9], zw[10], zw[11]);
+            dst[3] = make_uint4(zw[12], zw[13], zw[14], zw[15]);
+            const int dc = (int)(int8_t)(zw[0] & 0xFFu);
+            blockinfo[b] = (bits << 16) | ((uint32_t)dc & 0xFFFFu);
+        }
+        __syncwarp();
+    }
+
+    if (flagged_counter) {
+        nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);
+        nflag += __shfl_xor_sync(0xffffffffu, nflag, 8);
+        nflag += __shfl_xor_sync(0xffffffffu, nflag, 4);
+        nflag += __shfl_xor_sync(0xffffffffu, nflag, 2);
+        nflag += __shfl_xor_sync(0xffffffffu, nflag, 1);
+        if (lane == 0 && nflag) atomicAdd(flagged_counter, (unsigned long long)nflag);
+    }
+}
+
+}  // namespace jb

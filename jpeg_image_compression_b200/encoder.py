@@ -1,0 +1,131 @@
+"""Device-resident encoder: torch tensors for HBM buffers and streams, the C ABI for the work."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Batch, Stats, StripePacked, StripeSummary, check, load_library
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.JpegB200Error("no CUDA device: libjpegb200 has no CPU fallback")
+    return torch
+
+
+class DeviceEncoder:
+    """One encoder handle (workspace + tables) on one GPU."""
+
+    def __init__(self, device: int = 0, dct_mode: int = 0, bytes_per_block: int = 24):
+        self.torch = _torch()
+        self.lib = load_library()
+        self.device = device
+        self.handle = self.lib.jpegb200_encoder_create(device)
+        if not self.handle:
+            raise _lib.JpegB200Error("jpegb200_encoder_create: " + _lib.last_error())
+        check(self.lib.jpegb200_encoder_set_dct_mode(self.handle, dct_mode), "set_dct_mode")
+        check(self.lib.jpegb200_encoder_set_bytes_per_block(self.handle, bytes_per_block), "set_bytes_per_block")
+        self.bytes_per_block = bytes_per_block
+        self._scan = None
+        self._offsets = None
+
+    def close(self):
+        if self.handle:
+            self.lib.jpegb200_encoder_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- buffers -------------------------------------------------------------------
+    def scan_capacity(self, w: int, h: int, count: int) -> int:
+        nb = ((w + 7) // 8) * ((h + 7) // 8)
+        return count * (nb * self.bytes_per_block + 64) * 2
+
+    def _ensure_out(self, capacity: int, count: int):
+        t = self.torch
+        if self._scan is None or self._scan.numel() < capacity:
+            self._scan = t.empty(capacity, dtype=t.uint8, device=f"cuda:{self.device}")
+        if self._offsets is None or self._offsets.numel() < count + 1:
+            self._offsets = t.zeros(count + 1, dtype=t.int64, device=f"cuda:{self.device}")
+        return self._scan, self._offsets
+
+    # ---- encode --------------------------------------------------------------------
+    def encode_device(self, d_rgb, w: int, h: int, count: int = 1, image_stride: int = 0, scan=None, offsets=None):
+        """Launch the encode of `count` images resident in HBM (async on the current stream).
+        Returns (scan tensor, offsets tensor[count+1]) -- device tensors."""
+        if scan is None or offsets is None:
+            scan, offsets = self._ensure_out(self.scan_capacity(w, h, count), count)
+        b = Batch(d_rgb.data_ptr(), w, h, count, image_stride)
+        check(self.lib.jpegb200_encode_batch_device(self.handle, C.byref(b), scan.data_ptr(), scan.numel(),
+                                                    offsets.data_ptr(), self._stream()), "encode_batch_device")
+        return scan, offsets
+
+    def status(self):
+        check(self.lib.jpegb200_encoder_status(self.handle, self._stream()), "encoder_status")
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(self.lib.jpegb200_encoder_stats(self.handle, C.byref(s)), "encoder_stats")
+        return {"blocks": s.blocks, "flagged_coefficients": s.flagged_coefficients,
+                "kernel_launches": s.kernel_launches, "packed_bytes": s.packed_bytes}
+
+    def encode(self, rgb: np.ndarray) -> bytes:
+        """Host RGB (h,w,3) -> scan bytes through the device API (H2D, kernels, D2H)."""
+        scans = self.encode_batch(rgb[None])
+        return scans[0]
+
+    def encode_batch(self, rgbs: np.ndarray) -> list:
+        t = self.torch
+        rgbs = np.ascontiguousarray(rgbs, np.uint8)
+        n, h, w, _ = rgbs.shape
+        d = t.from_numpy(rgbs).to(f"cuda:{self.device}")
+        scan, offsets = self.encode_device(d, w, h, n)
+        self.status()
+        offs = offsets[: n + 1].cpu().numpy()
+        data = scan[: int(offs[n])].cpu().numpy().tobytes()
+        return [data[int(offs[i]): int(offs[i + 1])] for i in range(n)]
+
+    def coefficients(self, nblocks: int) -> np.ndarray:
+        out = np.empty((nblocks, 64), np.int16)
+        check(self.lib.jpegb200_encoder_read_coefficients(self.handle, out.ctypes.data, nblocks), "read_coefficients")
+        return out
+
+    def block_bits(self, nblocks: int) -> np.ndarray:
+        out = np.empty(nblocks, np.uint32)
+        check(self.lib.jpegb200_encoder_read_block_bits(self.handle, out.ctypes.data, nblocks), "read_block_bits")
+        return out
+
+    # ---- stripes -------------------------------------------------------------------
+    def stripe_analyze(self, d_rgb, w: int, stripe_h: int) -> dict:
+        s = StripeSummary()
+        check(self.lib.jpegb200_stripe_analyze(self.handle, d_rgb.data_ptr(), w, stripe_h, C.byref(s), self._stream()),
+              "stripe_analyze")
+        return {"first_dc": s.first_dc, "last_dc": s.last_dc, "bits_pred0": s.bits_pred0}
+
+    def stripe_pack(self, dc_pred: int, bit_begin: int) -> dict:
+        p = StripePacked()
+        check(self.lib.jpegb200_stripe_pack(self.handle, dc_pred, bit_begin, C.byref(p), self._stream()), "stripe_pack")
+        return {"bit_begin": p.bit_begin, "bit_end": p.bit_end, "head_byte": p.head_byte, "tail_byte": p.tail_byte}
+
+    def stripe_finish(self, or_last: int, owns_first: bool, is_last: bool, scan) -> int:
+        n = C.c_uint64(0)
+        check(self.lib.jpegb200_stripe_finish(self.handle, or_last, int(owns_first), int(is_last), scan.data_ptr(),
+                                              scan.numel(), C.byref(n), self._stream()), "stripe_finish")
+        return int(n.value)
+
+    # ---- synthetic inputs on the device --------------------------------------------
+    def synth(self, w: int, h: int, count: int = 1, seed0: int = 1, amp: int = 20):
+        t = self.torch
+        out = t.empty((count, h, w, 3), dtype=t.uint8, device=f"cuda:{self.device}")
+        check(self.lib.jpegb200_synth_rgb_device(out.data_ptr(), w, h, count, 0, seed0, amp, self._stream()), "synth")
+        return out

@@ -1,0 +1,235 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+  (1) the committed golden fixtures minted from the reference build,
+  (2) the oracle on fresh seeded inputs,
+  (3) SHA-256 of reference outputs on full-size synthetic images,
+bit-exact at every tap: quantized zig-zag coefficients, per-block bit costs, scan bytes, file."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import jpeg_image_compression_b200 as jb
+
+pytestmark = pytest.mark.gpu
+ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,
+                   7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38,
+                   31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def enc():
+    e = jb.DeviceEncoder(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def enc_exact():
+    e = jb.DeviceEncoder(0, dct_mode=1)
+    yield e
+    e.close()
+
+
+def _nblocks(rgb):
+    h, w, _ = rgb.shape
+    return ((h + 7) // 8) * ((w + 7) // 8)
+
+
+def test_golden_scan_coefficients_bits(enc, oracle, golden, golden_names):
+    for name in golden_names:
+        rgb = golden[f"{name}/rgb"]
+        scan = enc.encode(rgb)
+        nb = _nblocks(rgb)
+        zz = enc.coefficients(nb)
+        mism = int((zz != golden[f"{name}/zigzag"]).sum())
+        assert mism == 0, f"{name}: {mism} coefficient mismatches"
+        assert np.array_equal(enc.block_bits(nb), oracle.block_bits(golden[f"{name}/zigzag"])), name
+        assert scan == golden[f"{name}/scan"].tobytes(), name
+
+
+def test_golden_exact_mode(enc_exact, golden, golden_names):
+    for name in golden_names:
+        rgb = golden[f"{name}/rgb"]
+        assert enc_exact.encode(rgb) == golden[f"{name}/scan"].tobytes(), name
+        assert np.array_equal(enc_exact.coefficients(_nblocks(rgb)), golden[f"{name}/zigzag"]), name
+    st = enc_exact.stats()
+    assert st["flagged_coefficients"] == 63 * st["blocks"]
+
+
+def test_golden_fused_host_entry_and_file(golden, golden_names, tmp_path):
+    for name in golden_names:
+        rgb = golden[f"{name}/rgb"]
+        scan, first = jb.encode_scan_host(rgb, with_first_block=True)
+        assert scan == golden[f"{name}/scan"].tobytes(), name
+        raster = np.zeros(64, np.int16)
+        raster[ZIGZAG] = golden[f"{name}/zigzag"][0]
+        assert np.array_equal(first.reshape(64), raster), name
+        out = str(tmp_path / f"{name}.jpg")
+        assert jb.saveJPEGGrayscale(out, rgb)
+        assert open(out, "rb").read() == golden[f"{name}/file"].tobytes(), name
+
+
+def test_random_sizes_vs_oracle(enc, oracle):
+    rng = np.random.default_rng(2026)
+    dims = [(1, 1), (2, 9), (8, 8), (9, 9), (255, 8), (256, 8), (257, 8), (263, 17), (511, 33), (762, 40),
+            (1280, 24), (1283, 9), (64, 300), (5, 1031)]
+    for (w, h) in dims:
+        for kind in range(3):
+            if kind == 0:
+                rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            elif kind == 1:
+                rgb = oracle.synth_rgb(w, h, int(rng.integers(1 << 31)), int(rng.integers(0, 64)))
+            else:
+                base = rng.integers(0, 256, (1, 1, 3), dtype=np.uint8)
+                rgb = np.clip(base.astype(np.int32) + rng.integers(-3, 4, (h, w, 3)), 0, 255).astype(np.uint8)
+            scan = enc.encode(rgb)
+            zz = enc.coefficients(_nblocks(rgb))
+            ref_zz = oracle.coefficients(rgb)
+            assert int((zz != ref_zz).sum()) == 0, (w, h, kind)
+            assert scan == oracle.encode_scan(rgb), (w, h, kind)
+
+
+def test_extreme_blocks(enc, oracle):
+    """Saturated basis-function sign patterns (largest possible coefficients), flats, ties."""
+    blocks = []
+    r = np.arange(8)
+    for u in range(8):
+        for v in range(8):
+            pat = np.sign(np.outer(np.cos((2 * r + 1) * u * np.pi / 16), np.cos((2 * r + 1) * v * np.pi / 16)))
+            blocks.append(np.where(pat >= 0, 255, 0))
+            blocks.append(np.where(pat >= 0, 0, 255))
+    for v in (0, 1, 127, 128, 129, 254, 255):
+        blocks.append(np.full((8, 8), v))
+    img = np.concatenate([np.concatenate(blocks[i:i + 15], 1) for i in range(0, 135, 15)], 0).astype(np.uint8)
+    rgb = np.repeat(img[:, :, None], 3, 2)
+    assert enc.encode(rgb) == oracle.encode_scan(rgb)
+    assert np.array_equal(enc.coefficients(_nblocks(rgb)), oracle.coefficients(rgb))
+
+
+def test_fast_mode_equals_exact_mode_soak(enc, enc_exact):
+    """Randomised soak: guard-band path == reference-order path, coefficient for coefficient."""
+    total_flagged = total_blocks = 0
+    for seed, amp in [(11, 5), (12, 20), (13, 40), (14, 64), (15, 127)]:
+        d = enc.synth(1024, 1024, 1, seed, amp)
+        s1, o1 = enc.encode_device(d, 1024, 1024, 1)
+        enc.status()
+        a = enc.coefficients(128 * 128)
+        n1 = int(o1[1].item())
+        b1 = s1[:n1].cpu().numpy().tobytes()
+        st = enc.stats()
+        total_flagged += st["flagged_coefficients"]
+        total_blocks += st["blocks"]
+        s2, o2 = enc_exact.encode_device(d, 1024, 1024, 1)
+        enc_exact.status()
+        b = enc_exact.coefficients(128 * 128)
+        assert int((a != b).sum()) == 0, (seed, amp)
+        assert b1 == s2[: int(o2[1].item())].cpu().numpy().tobytes()
+    assert total_flagged < 0.01 * 63 * total_blocks          # the fallback must stay rare
+
+
+def test_device_synth_equals_host_synth(enc):
+    d = enc.synth(333, 77, 3, seed0=41, amp=20).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(d[i], jb.synth_rgb(333, 77, 41 + i, 20))
+
+
+def test_full_size_reference_hashes(enc, synth_hashes):
+    for key in ["1920x1080_seed0_amp20", "3840x2160_seed1_amp20", "3840x2160_seed1_amp0", "3840x2160_seed1_amp64",
+                "762x1309_seed5_amp20", "1283x725_seed9_amp20", "7680x4320_seed1_amp20"]:
+        e = synth_hashes[key]
+        d = enc.synth(e["w"], e["h"], 1, e["seed"], e["amp"])
+        assert hashlib.sha256(d.cpu().numpy().tobytes()).hexdigest() == e["rgb_sha256"], key
+        scan, offs = enc.encode_device(d, e["w"], e["h"], 1)
+        enc.status()
+        n = int(offs[1].item())
+        assert n == e["scan_bytes"], key
+        assert hashlib.sha256(scan[:n].cpu().numpy().tobytes()).hexdigest() == e["scan_sha256"], key
+        nb = ((e["w"] + 7) // 8) * ((e["h"] + 7) // 8)
+        assert hashlib.sha256(enc.coefficients(nb).tobytes()).hexdigest() == e["zigzag_sha256"], key
+
+
+def test_batch_equals_single(enc, oracle):
+    imgs = np.stack([oracle.synth_rgb(200, 120, s, 20) for s in range(7)])
+    scans = enc.encode_batch(imgs)
+    for i in range(7):
+        assert scans[i] == oracle.encode_scan(imgs[i]), i
+    # ragged geometry + noise in a batch
+    rng = np.random.default_rng(4)
+    imgs = rng.integers(0, 256, (5, 37, 51, 3), dtype=np.uint8)
+    scans = enc.encode_batch(imgs)
+    for i in range(5):
+        assert scans[i] == oracle.encode_scan(imgs[i]), i
+
+
+def test_batch_1080p_hashes(enc, synth_hashes):
+    d = enc.synth(1920, 1080, 66, 0, 20)
+    scan, offs = enc.encode_device(d, 1920, 1080, 66)
+    enc.status()
+    offs = offs[:67].cpu().numpy()
+    for i in (0, 64):
+        e = synth_hashes[f"1920x1080_seed{i}_amp20"]
+        b = scan[int(offs[i]): int(offs[i + 1])].cpu().numpy().tobytes()
+        assert len(b) == e["scan_bytes"] and hashlib.sha256(b).hexdigest() == e["scan_sha256"], i
+
+
+def test_workspace_overflow_is_reported_not_silent(oracle):
+    e = jb.DeviceEncoder(0, bytes_per_block=2)
+    rng = np.random.default_rng(1)
+    rgb = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    with pytest.raises(jb.JpegB200Error):
+        e.encode(rgb)
+    e.close()
+    # the host entry retries with the worst-case workspace and still matches
+    assert jb.encode_scan_host(rgb) == oracle.encode_scan(rgb)
+
+
+def test_stage_api_against_goldens(golden, golden_names, oracle):
+    from oracle.oracle import SYMBOL_DTYPE as ORC_SYM
+    for name in golden_names:
+        rgb = golden[f"{name}/rgb"]
+        y = jb.convertBMPToJPEGGrayscale(rgb)
+        assert np.array_equal(y, golden[f"{name}/y"]), name
+        c = jb.centerYImage(y)
+        assert np.array_equal(c, oracle.level_shift(golden[f"{name}/y"])), name
+        d = jb.performDCT(c)
+        assert np.array_equal(d.view(np.uint32), golden[f"{name}/dct"].view(np.uint32)), name
+        q = jb.quantizeImage(d)
+        z = jb.performZigZag(q)
+        assert np.array_equal(z, golden[f"{name}/zigzag"]), name
+        s = jb.performRLE(z)
+        g = golden[f"{name}/symbols"].astype(np.uint16)
+        assert np.array_equal(s["symbol"], g[:, 0]) and np.array_equal(s["code"], g[:, 1] | (g[:, 2] << 8)) \
+            and np.array_equal(s["codeBits"], g[:, 3]), name
+        assert jb.encodeHuffman(s, z.shape[0]) == golden[f"{name}/scan"].tobytes(), name
+    blk = np.arange(-32, 32, dtype=np.int8).reshape(8, 8)
+    assert np.array_equal(jb.computeDCTBlock(blk).view(np.uint32), oracle.fdct_block(blk).view(np.uint32))
+
+
+def test_stage_api_null_and_block_cap(oracle):
+    assert jb.convertBMPToJPEGGrayscale(None) is None and jb.performDCT(None) is None
+    rgb = oracle.synth_rgb(96, 64, 9, 30)
+    zz = oracle.coefficients(rgb)
+    sym = jb.performRLE(zz)
+    # totalBlocks smaller than the symbol stream: the reference stops after that many blocks
+    for nb in (1, 5, zz.shape[0]):
+        o_sym = oracle.rle(zz)
+        assert jb.encodeHuffman(sym, nb) == oracle.huffman(o_sym, nb).tobytes(), nb
+
+
+def test_cli_end_to_end(golden, tmp_path, ref):
+    from oracle.oracle import REF_APP, write_bmp
+    app = os.path.join(ROOT, "jpeg_image_compression_b200", "jpeg_compression_app")
+    for name in ["lena_crop256", "greenland_corner250x205", "one_pixel"]:
+        rgb = golden[f"{name}/rgb"]
+        bmp, out, out_ref = (str(tmp_path / f"{name}{s}") for s in (".bmp", ".jpg", "_ref.jpg"))
+        write_bmp(bmp, rgb)
+        r = subprocess.run([app, bmp, out], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.endswith("Save is sucesfull")
+        assert open(out, "rb").read() == golden[f"{name}/file"].tobytes(), name
+        if os.path.exists(REF_APP):                     # identical stdout chatter, file name aside
+            rr = subprocess.run([REF_APP, bmp, out_ref], capture_output=True, text=True)
+            assert rr.stdout.replace(out_ref, "X") == r.stdout.replace(out, "X")
+            assert open(out_ref, "rb").read() == open(out, "rb").read()
