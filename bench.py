@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the natural_c JPEG encode hot path on B200 (BASELINE.json metric:
+Mpixel/s BMP->JPEG encode; achieved HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (RGB pixels -> stuffed JPEG scan bytes) over one synthetic
+input.  Workloads (SURVEY.md section 8d generator, seed/amp as named there):
+    uhd4k      (default, BASELINE configs[1]) one 3840x2160 image per step per GPU; N>1 shards
+               images by rank, no data-path collective (weak scaling)
+    batch1080p a batch of 1920x1080 images per step, sharded by image across ranks
+The timed region holds exactly K steps, bracketed by barrier + synchronize, timed with CUDA events
+on the launching stream, max over ranks.  Inputs rotate through a ring of distinct images larger
+than L2 so every step reads its pixels from HBM.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified
+natural_c objects) on the host cores; see cpu_baseline in the printed line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mpixel/s BMP->JPEG encode (natural_c hot path)"
+UNIT = "Mpixel/s"
+W4K, H4K = 3840, 2160
+BAND_ROWS = 128            # reference arm: one 3840x128 band per thread per step
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML polled from a thread; the region can be short)
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.max_mhz, self.thread, self.ok = None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _poll(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while True:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            if self._stop.wait(0.005):
+                break
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+
+    def stop(self) -> dict:
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self.thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference CPU implementation (oracle/_ref) -- the one place bench.py may execute oracle/
+def _ref_encode_band_fn():
+    import ctypes as C
+    import numpy as np
+    from oracle.oracle import Oracle, Ref, _Img, have_ref
+    orc = Oracle()
+    if have_ref():
+        ref = Ref()
+        L = ref.lib
+
+        def encode(rgb: np.ndarray) -> int:
+            """the reference's own stage chain, exactly as saveJPEGGrayscale runs it
+            (natural_c/src/io/jpeg_handler.c:133-201), host RGB in, scan bytes out"""
+            h, w, _ = rgb.shape
+            bmp = _Img(w, h, rgb.ctypes.data)
+            y = L.convertBMPToJPEGGrayscale(C.byref(bmp))
+            c = L.centerYImage(y)
+            d = L.performDCT(c)
+            q = L.quantizeImage(d)
+            z = L.performZigZag(q)
+            r = L.performRLE(z)
+            b = L.encodeHuffman(r, z.contents.totalBlocks)
+            n = b.contents.size
+            L.freeJpegEncoderBuffer(b); L.freeRLEData(r); L.freeZigZagData(z); L.freeQuantizedImage(q)
+            L.freeDCTImage(d); L.freeCenteredYImage(c); L.freeYImage(y)
+            return n
+        # warm the reference's lazily initialised (non thread-safe) Huffman tables once
+        encode(np.zeros((8, 8, 3), np.uint8))
+        return encode, "reference", orc
+
+    def encode_port(rgb):
+        return len(orc.encode_scan(rgb))
+    return encode_port, "port", orc
+
+
+def time_reference(steps: int, warmup: int, threads: int):
+    """Each step: `threads` host threads each encode one 3840x128 band of the 4K workload image
+    with the reference's CPU code (ctypes releases the GIL).  Returns Mpixel/s and the kind."""
+    from concurrent.futures import ThreadPoolExecutor
+    encode, kind, orc = _ref_encode_band_fn()
+    full = orc.synth_rgb(W4K, H4K, 1, 20)
+    nbands = H4K // BAND_ROWS
+    bands = [full[i * BAND_ROWS:(i + 1) * BAND_ROWS].copy() for i in range(nbands)]
+    px_per_step = threads * W4K * BAND_ROWS
+    with ThreadPoolExecutor(threads) as pool:
+        def one_step(k):
+            list(pool.map(encode, [bands[(k * threads + t) % nbands] for t in range(threads)]))
+        for k in range(warmup):
+            one_step(k)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one_step(warmup + k)
+        dt = time.perf_counter() - t0
+    return px_per_step * steps / dt / 1e6, dt / steps * 1e3, kind, px_per_step
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    val, ms, kind, px = time_reference(args.steps, args.warmup, threads)
+    sample = (f"per step each of {threads} threads encodes one 3840x{BAND_ROWS} band of the synthetic "
+              f"3840x2160 image (seed=1, amp=20) with the reference natural_c core stages (-O2 build)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "uhd4k: synthetic 3840x2160 24-bit RGB, single image encode", "seed": 1, "amp": 20},
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import jpeg_image_compression_b200 as jb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libjpegb200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    enc = jb.DeviceEncoder(local_rank)
+
+    if args.workload == "uhd4k":
+        w, h, per_step, ring = W4K, H4K, 1, 8
+        wl_name = "uhd4k: synthetic 3840x2160 24-bit RGB, single image encode (BASELINE configs[1]); N>1: images sharded by rank"
+    elif args.workload == "batch1080p":
+        w, h, per_step, ring = 1920, 1080, args.batch, 2
+        wl_name = f"batch1080p: {args.batch} synthetic 1920x1080 images per step per GPU, sharded by image"
+    else:
+        raise SystemExit(f"unknown workload {args.workload}")
+    px_step = w * h * per_step
+    # ring of distinct inputs, larger than the 126 MB L2, generated on the device
+    seed0 = 1 + rank * 100000
+    inputs = [enc.synth(w, h, per_step, seed0 + i * per_step, 20) for i in range(ring)]
+    ring_bytes = sum(t.numel() for t in inputs)
+    cap = enc.scan_capacity(w, h, per_step)
+    outs = [(torch.empty(cap, dtype=torch.uint8, device=dev), torch.zeros(per_step + 1, dtype=torch.int64, device=dev))
+            for _ in range(ring)]
+
+    def step(i):
+        k = i % ring
+        enc.encode_device(inputs[k], w, h, per_step, scan=outs[k][0], offsets=outs[k][1])
+
+    # ---- warm-up (also sizes the workspace), parity spot-check, launch count -------------------
+    for i in range(max(args.warmup, ring)):
+        step(i)
+    torch.cuda.synchronize()
+    enc.status()
+    launches_per_step = enc.stats()["kernel_launches"]
+    scan_bytes = [int(o[per_step].item()) for _, o in outs]
+
+    # ---- CUDA graph of one ring revolution (4 kernels per image; launch-bound otherwise) --------
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(ring):
+                step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(ring):
+                step(i)
+        graph.replay()
+        torch.cuda.synchronize()
+        enc.status()
+
+    def run_steps(n):
+        if graph is not None:
+            full, rest = divmod(n, ring)
+            for _ in range(full):
+                graph.replay()
+            for i in range(rest):
+                step(i)
+        else:
+            for i in range(n):
+                step(i)
+
+    # ---- device-resident timing: exactly K steps --------------------------------------------------
+    run_steps(args.warmup)
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record()
+    run_steps(args.steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    enc.status()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = px_step * args.steps * world / (ms_total * 1e-3) / 1e6
+
+    # ---- per-kernel time of the dominant kernel (cudaEvents on the launching stream) -----------
+    enc.set_profiling(True)
+    enc.kernel_times(reset=True)
+    prof_steps = min(args.steps, 64)
+    for i in range(prof_steps):
+        step(i)
+    kt = enc.kernel_times(reset=True)
+    enc.set_profiling(False)
+    k1_ms = kt["ms"][0] / max(kt["calls"][0], 1)
+    step_ms_sum = sum(kt["ms"]) / prof_steps
+    mean_scan = sum(scan_bytes) / len(scan_bytes)
+    algo_bytes = 3.0 * px_step + mean_scan                 # A = 3*W*H + S per launch
+    peak, peak_src = measured_peak_gbs()
+    achieved = algo_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
+    if os.path.exists(tpath) and args.workload == "uhd4k":
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_fused_blocks", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(k1_ms, 5),
+                "kernel_share_of_step": round(k1_ms / step_ms_sum, 3) if step_ms_sum > 0 else None,
+                "per_kernel_ms": {n: round(m / max(c, 1), 5) for n, m, c in zip(kt["names"], kt["ms"], kt["calls"]) if c}}
+
+    # ---- end to end: pinned host buffers -> C-ABI call -> pinned host buffers --------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        if args.workload == "uhd4k":
+            pin_in = [inputs[i].cpu().pin_memory() for i in range(min(ring, 4))]
+            pin_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            e2e_steps = max(3, min(args.steps, 50))
+            for i in range(3):
+                enc.encode_host(pin_in[i % len(pin_in)], w, h, pin_out)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            d2h = 0
+            for i in range(e2e_steps):
+                d2h += enc.encode_host(pin_in[i % len(pin_in)], w, h, pin_out)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": round(px_step * e2e_steps * world / dt / 1e6, 1), "unit": UNIT,
+                   "h2d_bytes_per_step": 3 * px_step, "d2h_bytes_per_step": int(d2h / e2e_steps) + 16,
+                   "steps": e2e_steps, "api": "jpegb200_encode_host (C ABI, pinned host buffers, H2D + 4 kernels + D2H)"}
+        else:
+            # batch: pinned host batch -> device -> encode -> D2H of offsets + scan bytes
+            pin = inputs[0].cpu().pin_memory()
+            dbuf = torch.empty_like(inputs[0])
+            pin_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            e2e_steps = max(2, min(args.steps, 5))
+            t0 = None
+            for i in range(e2e_steps + 1):
+                if i == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                dbuf.copy_(pin, non_blocking=True)
+                s, o = enc.encode_device(dbuf, w, h, per_step, scan=outs[0][0], offsets=outs[0][1])
+                n = int(o[per_step].item())
+                pin_out[:n].copy_(s[:n], non_blocking=True)
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e = {"value": round(px_step * e2e_steps * world / dt / 1e6, 1), "unit": UNIT,
+                   "h2d_bytes_per_step": 3 * px_step, "d2h_bytes_per_step": n + 8 * (per_step + 1), "steps": e2e_steps,
+                   "api": "DeviceEncoder.encode_device with pinned H2D/D2H around jpegb200_encode_batch_device"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        encode, kind, orc = _ref_encode_band_fn()
+        full = orc.synth_rgb(W4K, H4K, 1, 20)
+        t0 = time.perf_counter()
+        n_img = 0
+        while True:
+            encode(full)
+            n_img += 1
+            if time.perf_counter() - t0 > 10.0 or n_img >= 12:
+                break
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": round(W4K * H4K * n_img / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": f"{n_img} full synthetic 3840x2160 images (seed=1, amp=20) through the reference's seven "
+                                  f"core stages, single thread (the reference is single-threaded), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "width": w, "height": h, "images_per_step_per_gpu": per_step, "seed": seed0,
+                       "amp": 20, "l2": f"inputs rotate through a ring of {ring} distinct device buffers "
+                                         f"({ring_bytes / 1e6:.0f} MB > 126 MB L2), no flush needed",
+                       "cuda_graph": bool(graph is not None), "scan_bytes_per_step": int(mean_scan)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="uhd4k", choices=["uhd4k", "batch1080p"])
+    ap.add_argument("--batch", type=int, default=512, help="images per step per GPU for batch1080p")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps == 2000 and args.warmup == 200:      # defaults: keep the CPU arm to about a minute
+            args.steps, args.warmup = 100, 5
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

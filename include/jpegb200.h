@@ -178,10 +178,11 @@ int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb200_batch *ba
                                  uint8_t *d_scan, uint64_t scan_capacity,
                                  uint64_t *d_scan_offsets, void *cuda_stream);
 
-/* Device error word of the last launch (0 = ok, else a JPEGB200_ERR_*); synchronises. */
+/* Device error word (sticky until read; 0 = ok, else a JPEGB200_ERR_*); synchronises the stream. */
 int jpegb200_encoder_status(jpegb200_encoder *enc, void *cuda_stream);
 
-/* Counters of the last launch (filled after jpegb200_encoder_status). */
+/* Counters.  blocks / kernel_launches / packed_bytes describe the last encode call;
+ * flagged_coefficients accumulates since the previous jpegb200_encoder_stats call. */
 typedef struct {
     uint64_t blocks;                /* 8x8 blocks processed                           */
     uint64_t flagged_coefficients;  /* coefficients re-evaluated in reference order    */
@@ -189,6 +190,19 @@ typedef struct {
     uint64_t packed_bytes;          /* unstuffed stream bytes (all images)             */
 } jpegb200_stats;
 int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out);
+
+/* Per-kernel device time: with profiling on, every kernel launch is bracketed by cudaEvents
+ * on the launching stream.  kernel ids: 0 fused block kernel, 1 bit-offset scan, 2 bit pack,
+ * 3 byte stuffing, 4 image layout, 5 shared-word clear.  Synchronises the device. */
+int jpegb200_encoder_set_profiling(jpegb200_encoder *enc, int on);
+int jpegb200_encoder_kernel_times(jpegb200_encoder *enc, double ms_total[8], uint64_t calls[8], int reset);
+
+/* Host buffers in, host buffers out (the reference-facing call with an explicit handle):
+ * H2D copy of the RGB payload, the four kernels, D2H copy of the stuffed scan.  Pinned caller
+ * buffers make the copies run at PCIe speed.  Synchronous. */
+int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_rgb, int width, int height,
+                         uint8_t *host_scan, uint64_t host_capacity, uint64_t *host_scan_bytes,
+                         void *cuda_stream);
 
 /* Stage taps for parity tests (device -> host copies; synchronous):
  * zig-zag coefficients of the last launch widened to int16 [count*blocks][64], and

@@ -139,7 +139,7 @@ __device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
 __global__ void __launch_bounds__(K1_THREADS, 2)
 k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blockinfo,
                const uint8_t *__restrict__ aclut_g, unsigned long long *__restrict__ flagged_counter,
-               const int exact_mode)
+               const int exact_mode, uint64_t *__restrict__ lookback_state, const uint64_t lookback_words)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *aclut = smem;
@@ -149,6 +149,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
 
     for (int i = threadIdx.x; i < ACLUT_BYTES / 16; i += K1_THREADS)
         reinterpret_cast<uint4 *>(aclut)[i] = reinterpret_cast<const uint4 *>(aclut_g)[i];
+    // reset the decoupled look-back state of the scan (K2) and stuffing (K4) kernels that
+    // follow in the stream: keeps a whole encode at four launches and CUDA-graph replayable
+    for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;
+         i += (uint64_t)gridDim.x * K1_THREADS)
+        lookback_state[i] = 0;
     __syncthreads();
 
     const uint64_t nwarps = (uint64_t)gridDim.x * K1_WARPS;

@@ -142,16 +142,21 @@ struct jpegb200_encoder {
     int sm_count = 148;
     int dct_mode = 0;
     int bytes_per_block = 24;
-    uint32_t epoch = 0;
-    jb::DeviceBuffer coef, blockinfo, blockoff, tilebase, scan_state, image_bits, image_base, packed, stuff_state,
-        image_ff, aclut, misc, stripe_offsets;
+    jb::DeviceBuffer coef, blockinfo, blockoff, tilebase, lookback, image_bits, image_base, packed, image_ff, aclut,
+        misc, host_in, host_scan;
     // last launch
     jb::EntropyArgs args{};
     jb::Geom geom{};
+    uint64_t lookback_words = 0;
     uint64_t total_blocks = 0;
     uint64_t launches = 0;
     bool stripe_ready = false;
-    uint64_t stripe_bit_begin = 0;
+    // optional per-kernel timing (cudaEvents on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;        // 2 per timed kernel of the last launch
+    std::vector<int> event_kernel;          // kernel id of each event pair
+    double kernel_ms[8] = {0};
+    uint64_t kernel_calls[8] = {0};
 };
 
 namespace jb {
@@ -199,16 +204,6 @@ static uint64_t *misc_offsets(jpegb200_encoder *e)
     return reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(e->misc.ptr) + 16);
 }
 
-static int next_epoch(jpegb200_encoder *enc, cudaStream_t st)
-{
-    if (++enc->epoch >= (1u << 22) - 1) {       // state words carry a 22-bit epoch: recycle
-        enc->epoch = 1;
-        if (enc->scan_state.ptr) JB_CUDA(cudaMemsetAsync(enc->scan_state.ptr, 0, enc->scan_state.bytes, st));
-        if (enc->stuff_state.ptr) JB_CUDA(cudaMemsetAsync(enc->stuff_state.ptr, 0, enc->stuff_state.bytes, st));
-    }
-    return JPEGB200_OK;
-}
-
 // Fill geometry + workspace for `count` images of w x h.
 static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, int count, uint64_t stride)
 {
@@ -238,12 +233,11 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     if ((rc = enc->coef.reserve(tb * 64))) return rc;
     if ((rc = enc->blockinfo.reserve(tb * 4))) return rc;
     if ((rc = enc->blockoff.reserve(tb * 4))) return rc;
-    const size_t old_scan = enc->scan_state.bytes, old_stuff = enc->stuff_state.bytes;
     if ((rc = enc->tilebase.reserve((uint64_t)tiles * count * 8))) return rc;
-    if ((rc = enc->scan_state.reserve((uint64_t)tiles * count * 8))) return rc;
-    if ((rc = enc->stuff_state.reserve((uint64_t)chunks_cap * count * 8))) return rc;
-    if (enc->scan_state.bytes != old_scan) JB_CUDA(cudaMemset(enc->scan_state.ptr, 0, enc->scan_state.bytes));
-    if (enc->stuff_state.bytes != old_stuff) JB_CUDA(cudaMemset(enc->stuff_state.ptr, 0, enc->stuff_state.bytes));
+    // look-back state of K2 (one word per scan tile) and K4 (one word per 4 KiB chunk), contiguous so
+    // that K1's prologue clears both
+    enc->lookback_words = (uint64_t)tiles * count + (uint64_t)chunks_cap * count;
+    if ((rc = enc->lookback.reserve(enc->lookback_words * 8))) return rc;
     if ((rc = enc->image_bits.reserve((uint64_t)count * 8))) return rc;
     if ((rc = enc->image_base.reserve((uint64_t)count * 8))) return rc;
     if ((rc = enc->image_ff.reserve((uint64_t)count * 8))) return rc;
@@ -254,12 +248,12 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.blockinfo = static_cast<const uint32_t *>(enc->blockinfo.ptr);
     a.blockoff = static_cast<uint32_t *>(enc->blockoff.ptr);
     a.tilebase = static_cast<uint64_t *>(enc->tilebase.ptr);
-    a.scan_state = static_cast<uint64_t *>(enc->scan_state.ptr);
+    a.scan_state = static_cast<uint64_t *>(enc->lookback.ptr);
     a.image_bits = static_cast<uint64_t *>(enc->image_bits.ptr);
     a.image_base = static_cast<uint64_t *>(enc->image_base.ptr);
     a.packed = static_cast<uint32_t *>(enc->packed.ptr);
     a.packed_capacity = packed_per_image * (uint64_t)count;
-    a.stuff_state = static_cast<uint64_t *>(enc->stuff_state.ptr);
+    a.stuff_state = static_cast<uint64_t *>(enc->lookback.ptr) + (uint64_t)tiles * count;
     a.image_ff = static_cast<uint64_t *>(enc->image_ff.ptr);
     a.scan = nullptr;
     a.scan_capacity = 0;
@@ -269,22 +263,47 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.tiles = tiles;
     a.chunks_cap = chunks_cap;
     a.count = count;
-    a.epoch = 0;
+    a.epoch = 1;
     a.dc_pred0 = 0;
     a.bit_phase = 0;
     return JPEGB200_OK;
 }
+
+// ---- kernel launches (optionally bracketed by cudaEvents for per-kernel timing) -----------
+
+enum KernelId { KID_BLOCK = 0, KID_SCAN = 1, KID_PACK = 2, KID_STUFF = 3, KID_LAYOUT = 4, KID_ZERO = 5 };
+
+struct TimedLaunch {
+    jpegb200_encoder *enc;
+    cudaStream_t st;
+    cudaEvent_t stop = nullptr;
+    TimedLaunch(jpegb200_encoder *e, cudaStream_t s, int kid) : enc(e), st(s)
+    {
+        ++enc->launches;
+        if (!enc->profiling) return;
+        cudaEvent_t start = nullptr;
+        if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) { stop = nullptr; return; }
+        enc->events.push_back(start);
+        enc->events.push_back(stop);
+        enc->event_kernel.push_back(kid);
+        cudaEventRecord(start, st);
+    }
+    ~TimedLaunch() { if (stop) cudaEventRecord(stop, st); }
+};
 
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
     const Geom &g = enc->geom;
     const uint64_t want = (g.total_strips + K1_WARPS - 1) / K1_WARPS;
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * 2);
-    k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
-                                                       static_cast<uint32_t *>(enc->blockinfo.ptr),
-                                                       static_cast<const uint8_t *>(enc->aclut.ptr),
-                                                       misc_flagged(enc), enc->dct_mode);
-    ++enc->launches;
+    {
+        TimedLaunch t(enc, st, KID_BLOCK);
+        k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
+                                                           static_cast<uint32_t *>(enc->blockinfo.ptr),
+                                                           static_cast<const uint8_t *>(enc->aclut.ptr), misc_flagged(enc),
+                                                           enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
+                                                           enc->lookback_words);
+    }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
 }
@@ -292,8 +311,10 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 static int launch_bit_scan(jpegb200_encoder *enc, cudaStream_t st)
 {
     const EntropyArgs &a = enc->args;
-    k_bit_scan<<<dim3(a.tiles, a.count), K2_THREADS, 0, st>>>(a);
-    ++enc->launches;
+    {
+        TimedLaunch t(enc, st, KID_SCAN);
+        k_bit_scan<<<dim3(a.tiles, a.count), K2_THREADS, 0, st>>>(a);
+    }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
 }
@@ -302,8 +323,10 @@ static int launch_pack(jpegb200_encoder *enc, cudaStream_t st)
 {
     const EntropyArgs &a = enc->args;
     const unsigned ptiles = (unsigned)((a.nb + K3_THREADS - 1) / K3_THREADS);
-    k_pack<<<dim3(ptiles, a.count), K3_THREADS, K3_SMEM_WORDS * 4, st>>>(a);
-    ++enc->launches;
+    {
+        TimedLaunch t(enc, st, KID_PACK);
+        k_pack<<<dim3(ptiles, a.count), K3_THREADS, K3_SMEM_WORDS * 4, st>>>(a);
+    }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
 }
@@ -311,9 +334,65 @@ static int launch_pack(jpegb200_encoder *enc, cudaStream_t st)
 static int launch_stuff(jpegb200_encoder *enc, const StuffArgs &sa, cudaStream_t st)
 {
     const EntropyArgs &a = enc->args;
-    k_stuff<<<dim3(a.chunks_cap, a.count), K4_THREADS, 0, st>>>(a, sa);
-    ++enc->launches;
+    {
+        TimedLaunch t(enc, st, KID_STUFF);
+        k_stuff<<<dim3(a.chunks_cap, a.count), K4_THREADS, 0, st>>>(a, sa);
+    }
     JB_CUDA(cudaGetLastError());
+    return JPEGB200_OK;
+}
+
+// fold finished event pairs into the per-kernel accumulators (requires the stream to be idle)
+static void harvest_events(jpegb200_encoder *enc)
+{
+    for (size_t i = 0; i < enc->event_kernel.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, enc->events[2 * i], enc->events[2 * i + 1]) == cudaSuccess) {
+            enc->kernel_ms[enc->event_kernel[i]] += ms;
+            enc->kernel_calls[enc->event_kernel[i]] += 1;
+        }
+        cudaEventDestroy(enc->events[2 * i]);
+        cudaEventDestroy(enc->events[2 * i + 1]);
+    }
+    enc->events.clear();
+    enc->event_kernel.clear();
+}
+
+static int encode_launch(jpegb200_encoder *enc, uint8_t *d_scan, uint64_t scan_capacity, uint64_t *d_scan_offsets,
+                         cudaStream_t st)
+{
+    int rc = 0;
+    enc->launches = 0;
+    enc->stripe_ready = false;
+    EntropyArgs &a = enc->args;
+    a.scan = d_scan;
+    a.scan_capacity = scan_capacity;
+    a.scan_offsets = d_scan_offsets;
+    if ((rc = launch_block_kernel(enc, st))) return rc;
+    if ((rc = launch_bit_scan(enc, st))) return rc;
+    if (a.count == 1) {
+        if ((rc = launch_pack(enc, st))) return rc;
+        if ((rc = launch_stuff(enc, StuffArgs{0, 0, 0}, st))) return rc;
+    } else {
+        {
+            TimedLaunch t(enc, st, KID_LAYOUT);
+            k_image_layout<<<1, 1024, 0, st>>>(a, 0);
+        }
+        const uint64_t ptiles = (a.nb + K3_THREADS - 1) / K3_THREADS * (uint64_t)a.count;
+        {
+            TimedLaunch t(enc, st, KID_ZERO);
+            k_zero_shared_words<<<(unsigned)((ptiles + 255) / 256), 256, 0, st>>>(a);
+        }
+        JB_CUDA(cudaGetLastError());
+        if ((rc = launch_pack(enc, st))) return rc;
+        if ((rc = launch_stuff(enc, StuffArgs{1, 0, 0}, st))) return rc;
+        {
+            TimedLaunch t(enc, st, KID_LAYOUT);
+            k_image_layout<<<1, 1024, 0, st>>>(a, 1);
+        }
+        JB_CUDA(cudaGetLastError());
+        if ((rc = launch_stuff(enc, StuffArgs{2, 0, 0}, st))) return rc;
+    }
     return JPEGB200_OK;
 }
 
@@ -360,9 +439,11 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
 {
     if (!enc) return;
     cudaSetDevice(enc->device);
-    for (DeviceBuffer *b : {&enc->coef, &enc->blockinfo, &enc->blockoff, &enc->tilebase, &enc->scan_state,
-                            &enc->image_bits, &enc->image_base, &enc->packed, &enc->stuff_state, &enc->image_ff,
-                            &enc->aclut, &enc->misc, &enc->stripe_offsets})
+    cudaDeviceSynchronize();
+    harvest_events(enc);
+    for (DeviceBuffer *b : {&enc->coef, &enc->blockinfo, &enc->blockoff, &enc->tilebase, &enc->lookback, &enc->image_bits,
+                            &enc->image_base, &enc->packed, &enc->image_ff, &enc->aclut, &enc->misc, &enc->host_in,
+                            &enc->host_scan})
         b->release();
     delete enc;
 }
@@ -381,6 +462,27 @@ extern "C" int jpegb200_encoder_set_bytes_per_block(jpegb200_encoder *enc, int b
     return JPEGB200_OK;
 }
 
+extern "C" int jpegb200_encoder_set_profiling(jpegb200_encoder *enc, int on)
+{
+    if (!enc) return JPEGB200_ERR_ARG;
+    enc->profiling = on != 0;
+    return JPEGB200_OK;
+}
+
+extern "C" int jpegb200_encoder_kernel_times(jpegb200_encoder *enc, double ms_total[8], uint64_t calls[8], int reset)
+{
+    if (!enc || !ms_total || !calls) return JPEGB200_ERR_ARG;
+    JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    harvest_events(enc);
+    for (int i = 0; i < 8; ++i) {
+        ms_total[i] = enc->kernel_ms[i];
+        calls[i] = enc->kernel_calls[i];
+        if (reset) { enc->kernel_ms[i] = 0; enc->kernel_calls[i] = 0; }
+    }
+    return JPEGB200_OK;
+}
+
 extern "C" int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb200_batch *batch, uint8_t *d_scan,
                                             uint64_t scan_capacity, uint64_t *d_scan_offsets, void *cuda_stream)
 {
@@ -391,36 +493,10 @@ extern "C" int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb20
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int rc = prepare(enc, batch->d_rgb, batch->width, batch->height, batch->count, batch->image_stride);
     if (rc) return rc;
-    if ((rc = next_epoch(enc, st))) return rc;
-    enc->launches = 0;
-    enc->stripe_ready = false;
-    EntropyArgs &a = enc->args;
-    a.epoch = enc->epoch;
-    a.scan = d_scan;
-    a.scan_capacity = scan_capacity;
-    a.scan_offsets = d_scan_offsets;
-    JB_CUDA(cudaMemsetAsync(enc->misc.ptr, 0, 16, st));
-    if ((rc = launch_block_kernel(enc, st))) return rc;
-    if ((rc = launch_bit_scan(enc, st))) return rc;
-    if (a.count == 1) {
-        if ((rc = launch_pack(enc, st))) return rc;
-        if ((rc = launch_stuff(enc, StuffArgs{0, 0, 0}, st))) return rc;
-    } else {
-        k_image_layout<<<1, 1024, 0, st>>>(a, 0);
-        const uint64_t ptiles = (a.nb + K3_THREADS - 1) / K3_THREADS * (uint64_t)a.count;
-        k_zero_shared_words<<<(unsigned)((ptiles + 255) / 256), 256, 0, st>>>(a);
-        enc->launches += 2;
-        JB_CUDA(cudaGetLastError());
-        if ((rc = launch_pack(enc, st))) return rc;
-        if ((rc = launch_stuff(enc, StuffArgs{1, 0, 0}, st))) return rc;
-        k_image_layout<<<1, 1024, 0, st>>>(a, 1);
-        ++enc->launches;
-        JB_CUDA(cudaGetLastError());
-        if ((rc = launch_stuff(enc, StuffArgs{2, 0, 0}, st))) return rc;
-    }
-    return JPEGB200_OK;
+    return encode_launch(enc, d_scan, scan_capacity, d_scan_offsets, st);
 }
 
+// Device error word (sticky until read): 0 = ok, else a JPEGB200_ERR_*.  Synchronises the stream.
 extern "C" int jpegb200_encoder_status(jpegb200_encoder *enc, void *cuda_stream)
 {
     if (!enc) return JPEGB200_ERR_ARG;
@@ -429,18 +505,22 @@ extern "C" int jpegb200_encoder_status(jpegb200_encoder *enc, void *cuda_stream)
     JB_CUDA(cudaSetDevice(enc->device));
     JB_CUDA(cudaMemcpyAsync(&err, misc_err(enc), 4, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
+    if (err) JB_CUDA(cudaMemsetAsync(misc_err(enc), 0, 4, st));
     if (err & ERRBIT_LOOKBACK) { g_last_error = "look-back spin limit hit"; return JPEGB200_ERR_INTERNAL; }
     if (err & ERRBIT_WORKSPACE) { g_last_error = "packed-bits workspace too small"; return JPEGB200_ERR_WORKSPACE; }
     if (err & ERRBIT_OUTPUT) { g_last_error = "scan buffer too small"; return JPEGB200_ERR_OUTPUT; }
     return JPEGB200_OK;
 }
 
+// Counters: flagged_coefficients accumulates since the last call (read-and-reset).
 extern "C" int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out)
 {
     if (!enc || !out) return JPEGB200_ERR_ARG;
     JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
     unsigned long long flagged = 0;
     JB_CUDA(cudaMemcpy(&flagged, misc_flagged(enc), 8, cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemset(misc_flagged(enc), 0, 8));
     out->blocks = enc->total_blocks;
     out->flagged_coefficients = flagged;
     out->kernel_launches = enc->launches;
@@ -457,6 +537,7 @@ extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t
 {
     if (!enc || !host_zz || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
     JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
     std::vector<int8_t> tmp((size_t)nblocks * 64);
     JB_CUDA(cudaMemcpy(tmp.data(), enc->coef.ptr, tmp.size(), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < tmp.size(); ++i) host_zz[i] = tmp[i];
@@ -467,6 +548,7 @@ extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t 
 {
     if (!enc || !host_bits || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
     JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
     // bit cost of block b = offset(b+1) - offset(b) within its image
     const EntropyArgs &a = enc->args;
     std::vector<uint32_t> off((size_t)enc->total_blocks);
@@ -492,10 +574,7 @@ extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_r
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int rc = prepare(enc, d_rgb, width, stripe_height, 1, 0);
     if (rc) return rc;
-    if ((rc = next_epoch(enc, st))) return rc;
     enc->launches = 0;
-    enc->args.epoch = enc->epoch;
-    JB_CUDA(cudaMemsetAsync(enc->misc.ptr, 0, 16, st));
     if ((rc = launch_block_kernel(enc, st))) return rc;
     // pass 1 of the scan with predictor 0 only to learn the stripe's total; offsets are
     // recomputed in jpegb200_stripe_pack once the true predictor and bit phase are known.
@@ -525,15 +604,12 @@ extern "C" int jpegb200_stripe_pack(jpegb200_encoder *enc, int16_t dc_predictor,
     }
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     JB_CUDA(cudaSetDevice(enc->device));
-    int rc = next_epoch(enc, st);
-    if (rc) return rc;
     EntropyArgs &a = enc->args;
-    a.epoch = enc->epoch;
     a.dc_pred0 = dc_predictor;
     a.bit_phase = (uint32_t)(bit_begin & 7u);
-    const uint64_t packed_per_image = ((a.nb * (uint64_t)enc->bytes_per_block + 15) & ~15ull) + 32;
-    a.packed_capacity = packed_per_image;
-    enc->stripe_bit_begin = bit_begin;
+    a.packed_capacity = ((a.nb * (uint64_t)enc->bytes_per_block + 15) & ~15ull) + 32;
+    JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));   // second scan over the same tiles
+    int rc = 0;
     if ((rc = launch_bit_scan(enc, st))) return rc;
     if ((rc = launch_pack(enc, st))) return rc;
     uint64_t bits = 0;
@@ -560,14 +636,12 @@ extern "C" int jpegb200_stripe_finish(jpegb200_encoder *enc, uint32_t or_into_la
     if (!enc || !d_scan || !host_scan_bytes || !enc->stripe_ready) return JPEGB200_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     JB_CUDA(cudaSetDevice(enc->device));
-    int rc = next_epoch(enc, st);
-    if (rc) return rc;
     EntropyArgs &a = enc->args;
-    a.epoch = enc->epoch;
     a.scan = d_scan;
     a.scan_capacity = scan_capacity;
     a.scan_offsets = misc_offsets(enc);
     JB_CUDA(cudaMemsetAsync(misc_offsets(enc), 0, 16, st));
+    int rc = 0;
     if ((rc = launch_stuff(enc, StuffArgs{0, owns_first_byte ? 0u : 1u, or_into_last_byte & 0xFFu}, st))) return rc;
     uint64_t offs[2] = {0, 0};
     JB_CUDA(cudaMemcpyAsync(offs, misc_offsets(enc), 16, cudaMemcpyDeviceToHost, st));
@@ -590,7 +664,50 @@ extern "C" int jpegb200_synth_rgb_device(uint8_t *d_rgb, int width, int height, 
     return JPEGB200_OK;
 }
 
-// ---- C ABI: fused host entry ----------------------------------------------------------
+// ---- C ABI: host buffers in, host buffers out ----------------------------------------------
+//
+// The reference-facing call: RGB in host memory -> stuffed scan bytes in host memory.  The
+// handle keeps its device staging buffers between calls; H2D and D2H are inside the call.
+// If the caller's buffers are pinned (cudaHostAlloc / cudaHostRegister) the copies run at
+// PCIe speed, otherwise the driver stages them.
+
+extern "C" int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_rgb, int width, int height,
+                                    uint8_t *host_scan, uint64_t host_capacity, uint64_t *host_scan_bytes,
+                                    void *cuda_stream)
+{
+    if (!enc || !host_rgb || !host_scan || !host_scan_bytes || width <= 0 || height <= 0) {
+        g_last_error = "bad argument";
+        return JPEGB200_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    JB_CUDA(cudaSetDevice(enc->device));
+    const size_t nrgb = (size_t)width * (size_t)height * 3u;
+    const uint64_t nb = (uint64_t)((width + 7) / 8) * (uint64_t)((height + 7) / 8);
+    const uint64_t cap = 2 * (nb * (uint64_t)enc->bytes_per_block + 64);   // stuffed <= 2 x packed
+    int rc = 0;
+    if ((rc = enc->host_in.reserve(nrgb + 64))) return rc;
+    if ((rc = enc->host_scan.reserve(cap + 64))) return rc;
+    uint8_t *d_rgb = static_cast<uint8_t *>(enc->host_in.ptr);
+    uint8_t *d_scan = static_cast<uint8_t *>(enc->host_scan.ptr);
+    uint64_t *d_off = misc_offsets(enc);
+    JB_CUDA(cudaMemcpyAsync(d_rgb, host_rgb, nrgb, cudaMemcpyHostToDevice, st));
+    if ((rc = prepare(enc, d_rgb, width, height, 1, 0))) return rc;
+    if ((rc = encode_launch(enc, d_scan, cap, d_off, st))) return rc;
+    uint64_t offs[2] = {0, 0};
+    uint32_t err = 0;
+    JB_CUDA(cudaMemcpyAsync(offs, d_off, 16, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaMemcpyAsync(&err, misc_err(enc), 4, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    if (err) return jpegb200_encoder_status(enc, cuda_stream);
+    *host_scan_bytes = offs[1];
+    if (offs[1] > host_capacity) {
+        g_last_error = "host scan buffer too small";
+        return JPEGB200_ERR_OUTPUT;
+    }
+    JB_CUDA(cudaMemcpyAsync(host_scan, d_scan, offs[1], cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    return JPEGB200_OK;
+}
 
 namespace jb {
 static std::mutex g_default_mutex;
@@ -614,62 +731,35 @@ extern "C" JpegEncoderBuffer *jpegb200_encode_scan_dbg(const BMPImage *image, in
     std::lock_guard<std::mutex> lock(g_default_mutex);
     jpegb200_encoder *enc = default_encoder();
     if (!enc) return nullptr;
-    const size_t nrgb = (size_t)image->width * (size_t)image->height * 3u;
-    uint8_t *d_rgb = nullptr, *d_scan = nullptr;
-    uint64_t *d_off = nullptr;
-    JpegEncoderBuffer *result = nullptr;
-    uint8_t *host = nullptr;
     const uint64_t nb = (uint64_t)((image->width + 7) / 8) * (uint64_t)((image->height + 7) / 8);
-    for (int attempt = 0; attempt < 2 && !result; ++attempt) {
-        // stuffed size <= 2 x packed size; the packed size is bounded by the workspace setting
+    for (int attempt = 0; attempt < 2; ++attempt) {
         const uint64_t cap = 2 * (nb * (uint64_t)enc->bytes_per_block + 64);
-        bool ok = cuda_ok(cudaMalloc((void **)&d_rgb, nrgb + 64), "cudaMalloc(rgb)") &&
-                  cuda_ok(cudaMalloc((void **)&d_scan, cap), "cudaMalloc(scan)") &&
-                  cuda_ok(cudaMalloc((void **)&d_off, 16), "cudaMalloc(offsets)") &&
-                  cuda_ok(cudaMemcpy(d_rgb, image->data, nrgb, cudaMemcpyHostToDevice), "cudaMemcpy(H2D rgb)");
-        int rc = JPEGB200_ERR_CUDA;
-        if (ok) {
-            jpegb200_batch b{d_rgb, image->width, image->height, 1, 0};
-            rc = jpegb200_encode_batch_device(enc, &b, d_scan, cap, d_off, nullptr);
-            if (rc == JPEGB200_OK) rc = jpegb200_encoder_status(enc, nullptr);
-        }
+        uint8_t *host = (uint8_t *)malloc(cap);
+        JpegEncoderBuffer *result = (JpegEncoderBuffer *)malloc(sizeof(JpegEncoderBuffer));
+        uint64_t n = 0;
+        int rc = JPEGB200_ERR_INTERNAL;
+        if (host && result) rc = jpegb200_encode_host(enc, image->data, image->width, image->height, host, cap, &n, nullptr);
         if (rc == JPEGB200_OK) {
-            uint64_t offs[2] = {0, 0};
-            ok = cuda_ok(cudaMemcpy(offs, d_off, 16, cudaMemcpyDeviceToHost), "cudaMemcpy(D2H offsets)");
-            if (ok) {
-                host = (uint8_t *)malloc(offs[1] ? offs[1] : 1);
-                result = (JpegEncoderBuffer *)malloc(sizeof(JpegEncoderBuffer));
-                if (host && result && cuda_ok(cudaMemcpy(host, d_scan, offs[1], cudaMemcpyDeviceToHost), "cudaMemcpy(D2H scan)")) {
-                    result->data = host;
-                    result->size = offs[1];
-                    result->capacity = offs[1] ? offs[1] : 1;
-                    if (first_block) {
-                        int8_t zz[64];
-                        if (cuda_ok(cudaMemcpy(zz, enc->coef.ptr, 64, cudaMemcpyDeviceToHost), "cudaMemcpy(D2H block0)"))
-                            for (int k = 0; k < 64; ++k) first_block[kZigzag[k]] = zz[k];
-                    }
-                } else {
-                    free(host);
-                    free(result);
-                    result = nullptr;
-                }
+            if (first_block) {
+                int8_t zz[64];
+                if (cuda_ok(cudaMemcpy(zz, enc->coef.ptr, 64, cudaMemcpyDeviceToHost), "cudaMemcpy(D2H block0)"))
+                    for (int k = 0; k < 64; ++k) first_block[kZigzag[k]] = zz[k];
             }
+            result->data = host;
+            result->size = n;
+            result->capacity = cap;
+            return result;
         }
-        cudaFree(d_rgb);
-        cudaFree(d_scan);
-        cudaFree(d_off);
-        d_rgb = d_scan = nullptr;
-        d_off = nullptr;
-        if (!result && (rc == JPEGB200_ERR_WORKSPACE || rc == JPEGB200_ERR_OUTPUT) && attempt == 0) {
+        free(host);
+        free(result);
+        if ((rc == JPEGB200_ERR_WORKSPACE || rc == JPEGB200_ERR_OUTPUT) && attempt == 0) {
             enc->bytes_per_block = 184;              // worst case: 1463 bits per block
             continue;
         }
-        if (!result) {
-            fprintf(stderr, "jpegb200: encode failed: %s\n", g_last_error.c_str());
-            break;
-        }
+        fprintf(stderr, "jpegb200: encode failed: %s\n", g_last_error.c_str());
+        break;
     }
-    return result;
+    return nullptr;
 }
 
 extern "C" JpegEncoderBuffer *jpegb200_encode_scan(const BMPImage *image)

@@ -95,6 +95,27 @@ class DeviceEncoder:
         data = scan[: int(offs[n])].cpu().numpy().tobytes()
         return [data[int(offs[i]): int(offs[i + 1])] for i in range(n)]
 
+    def encode_host(self, host_rgb, w: int, h: int, host_scan) -> int:
+        """jpegb200_encode_host: host RGB buffer -> host scan buffer (H2D + kernels + D2H inside).
+        Buffers are numpy arrays or (preferably pinned) CPU torch tensors.  Returns the byte count."""
+        def ptr(x):
+            return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+        cap = host_scan.numel() if hasattr(host_scan, "numel") else host_scan.size
+        n = C.c_uint64(0)
+        check(self.lib.jpegb200_encode_host(self.handle, ptr(host_rgb), w, h, ptr(host_scan), cap, C.byref(n),
+                                            self._stream()), "encode_host")
+        return int(n.value)
+
+    def set_profiling(self, on: bool):
+        check(self.lib.jpegb200_encoder_set_profiling(self.handle, int(on)), "set_profiling")
+
+    def kernel_times(self, reset: bool = False) -> dict:
+        ms = (C.c_double * 8)()
+        calls = (C.c_uint64 * 8)()
+        check(self.lib.jpegb200_encoder_kernel_times(self.handle, ms, calls, int(reset)), "kernel_times")
+        return {"ms": list(ms), "calls": [int(c) for c in calls],
+                "names": ["fused_block", "bit_scan", "pack", "stuff", "image_layout", "zero_words", "", ""]}
+
     def coefficients(self, nblocks: int) -> np.ndarray:
         out = np.empty((nblocks, 64), np.int16)
         check(self.lib.jpegb200_encoder_read_coefficients(self.handle, out.ctypes.data, nblocks), "read_coefficients")

@@ -51,12 +51,13 @@ def test_golden_scan_coefficients_bits(enc, oracle, golden, golden_names):
 
 
 def test_golden_exact_mode(enc_exact, golden, golden_names):
+    enc_exact.stats()                                   # read-and-reset the flagged counter
     for name in golden_names:
         rgb = golden[f"{name}/rgb"]
         assert enc_exact.encode(rgb) == golden[f"{name}/scan"].tobytes(), name
         assert np.array_equal(enc_exact.coefficients(_nblocks(rgb)), golden[f"{name}/zigzag"]), name
-    st = enc_exact.stats()
-    assert st["flagged_coefficients"] == 63 * st["blocks"]
+        st = enc_exact.stats()
+        assert st["flagged_coefficients"] == 63 * st["blocks"], name
 
 
 def test_golden_fused_host_entry_and_file(golden, golden_names, tmp_path):
@@ -112,6 +113,7 @@ def test_extreme_blocks(enc, oracle):
 def test_fast_mode_equals_exact_mode_soak(enc, enc_exact):
     """Randomised soak: guard-band path == reference-order path, coefficient for coefficient."""
     total_flagged = total_blocks = 0
+    enc.stats()
     for seed, amp in [(11, 5), (12, 20), (13, 40), (14, 64), (15, 127)]:
         d = enc.synth(1024, 1024, 1, seed, amp)
         s1, o1 = enc.encode_device(d, 1024, 1024, 1)
@@ -128,6 +130,54 @@ def test_fast_mode_equals_exact_mode_soak(enc, enc_exact):
         assert int((a != b).sum()) == 0, (seed, amp)
         assert b1 == s2[: int(o2[1].item())].cpu().numpy().tobytes()
     assert total_flagged < 0.01 * 63 * total_blocks          # the fallback must stay rare
+
+
+def test_encode_host_pinned_buffers(enc, oracle):
+    import torch
+    rgb = oracle.synth_rgb(640, 360, 21, 20)
+    pin_in = torch.from_numpy(rgb).pin_memory()
+    pin_out = torch.empty(enc.scan_capacity(640, 360, 1), dtype=torch.uint8).pin_memory()
+    n = enc.encode_host(pin_in, 640, 360, pin_out)
+    assert pin_out[:n].numpy().tobytes() == oracle.encode_scan(rgb)
+    # pageable numpy buffers take the same path
+    out = np.empty(enc.scan_capacity(640, 360, 1), np.uint8)
+    n = enc.encode_host(rgb, 640, 360, out)
+    assert out[:n].tobytes() == oracle.encode_scan(rgb)
+
+
+def test_kernel_timing_taps(enc):
+    d = enc.synth(1024, 512, 1, 3, 20)
+    enc.set_profiling(True)
+    enc.kernel_times(reset=True)
+    for _ in range(3):
+        enc.encode_device(d, 1024, 512, 1)
+    t = enc.kernel_times(reset=True)
+    enc.set_profiling(False)
+    assert t["calls"][:4] == [3, 3, 3, 3] and all(ms > 0 for ms in t["ms"][:4])
+
+
+def test_cuda_graph_replay_is_correct(enc, oracle):
+    """The four-kernel encode is graph-capturable: look-back state is reset by K1 itself."""
+    import torch
+    rgbs = [oracle.synth_rgb(512, 256, s, 25) for s in (1, 2)]
+    d = [torch.from_numpy(r).cuda() for r in rgbs]
+    cap = enc.scan_capacity(512, 256, 1)
+    outs = [(torch.empty(cap, dtype=torch.uint8, device="cuda"), torch.zeros(2, dtype=torch.int64, device="cuda")) for _ in d]
+    for di, (s, o) in zip(d, outs):                       # warm-up: allocates the workspace
+        enc.encode_device(di, 512, 256, 1, scan=s, offsets=o)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for di, (s, o) in zip(d, outs):
+            enc.encode_device(di, 512, 256, 1, scan=s, offsets=o)
+    for _ in range(3):
+        for s, o in outs:
+            s.zero_(); o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        enc.status()
+        for r, (s, o) in zip(rgbs, outs):
+            assert s[: int(o[1].item())].cpu().numpy().tobytes() == oracle.encode_scan(r)
 
 
 def test_device_synth_equals_host_synth(enc):
