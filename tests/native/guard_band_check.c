@@ -1,0 +1,95 @@
+/* guard_band_check.c -- CPU emulation of the fused kernel's butterfly DCT (same operation
+ * order and FMA placement as jpeg_image_compression_b200/csrc/fused_block.cuh:dct8) against the
+ * reference-order sum (oracle/jpeg_oracle.c:orc_fdct_block without the final scale).
+ *
+ * Prints  max over blocks and coefficients of |s_ref - g*T| / sum|p|  which must stay below
+ * kGamma = 1e-5 (the guard half-width used on the device), for several input families.
+ * usage: guard_band_check <nblocks> <seed>
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+static const float k_cos[8][8] = {
+    {1.000000f, 0.980785f, 0.923880f, 0.831470f, 0.707107f, 0.555570f, 0.382683f, 0.195090f},
+    {1.000000f, 0.831470f, 0.382683f, -0.195090f, -0.707107f, -0.980785f, -0.923880f, -0.555570f},
+    {1.000000f, 0.555570f, -0.382683f, -0.980785f, -0.707107f, 0.195090f, 0.923880f, 0.831470f},
+    {1.000000f, 0.195090f, -0.923880f, -0.555570f, 0.707107f, 0.831470f, -0.382683f, -0.980785f},
+    {1.000000f, -0.195090f, -0.923880f, 0.555570f, 0.707107f, -0.831470f, -0.382684f, 0.980785f},
+    {1.000000f, -0.555570f, -0.382684f, 0.980785f, -0.707107f, -0.195090f, 0.923880f, -0.831470f},
+    {1.000000f, -0.831470f, 0.382684f, 0.195091f, -0.707107f, 0.980785f, -0.923879f, 0.555570f},
+    {1.000000f, -0.980785f, 0.923880f, -0.831470f, 0.707107f, -0.555570f, 0.382684f, -0.195090f}};
+
+static void dct8(float *x0, float *x1, float *x2, float *x3, float *x4, float *x5, float *x6, float *x7)
+{
+    const float C1 = 0.98078528040323044913f, C3 = 0.83146961230254523708f;
+    const float C5 = 0.55557023301960222474f, C7 = 0.19509032201612826785f;
+    const float TAN = 0.41421356237309504880f;
+    const float a0 = *x0 + *x7, a1 = *x1 + *x6, a2 = *x2 + *x5, a3 = *x3 + *x4;
+    const float b0 = *x0 - *x7, b1 = *x1 - *x6, b2 = *x2 - *x5, b3 = *x3 - *x4;
+    const float e0 = a0 + a3, e1 = a1 + a2, d0 = a0 - a3, d1 = a1 - a2;
+    *x0 = e0 + e1;
+    *x4 = e0 - e1;
+    *x2 = fmaf(d1, TAN, d0);
+    *x6 = fmaf(d0, TAN, -d1);
+    *x1 = fmaf(b3, C7, fmaf(b2, C5, fmaf(b1, C3, b0 * C1)));
+    *x3 = fmaf(b3, -C5, fmaf(b2, -C1, fmaf(b1, -C7, b0 * C3)));
+    *x5 = fmaf(b3, C3, fmaf(b2, C7, fmaf(b1, -C1, b0 * C5)));
+    *x7 = fmaf(b3, -C1, fmaf(b2, C3, fmaf(b1, -C5, b0 * C7)));
+}
+
+static uint64_t rng_state;
+static uint32_t rnd(void)
+{
+    rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)(rng_state >> 33);
+}
+
+int main(int argc, char **argv)
+{
+    const long nblocks = argc > 1 ? atol(argv[1]) : 100000;
+    rng_state = argc > 2 ? (uint64_t)atoll(argv[2]) : 1;
+    const double g[8] = {1.0, 1.0, cos(M_PI / 8), 1.0, cos(M_PI / 4), 1.0, cos(M_PI / 8), 1.0};
+    double worst = 0.0;
+    for (long n = 0; n < nblocks; ++n) {
+        int p[8][8];
+        const int family = (int)(n % 5);
+        const int base = (int)(rnd() % 256), amp = 1 + (int)(rnd() % 128);
+        for (int r = 0; r < 8; ++r)
+            for (int c = 0; c < 8; ++c) {
+                int v;
+                switch (family) {
+                case 0: v = (int)(rnd() % 256); break;                                  /* noise          */
+                case 1: v = base + (int)(rnd() % (2 * amp + 1)) - amp; break;             /* flat + noise   */
+                case 2: v = (rnd() & 1) ? 255 : 0; break;                                 /* saturated      */
+                case 3: v = base + (r * amp) / 8 + (c * amp) / 5; break;                  /* ramp           */
+                default: v = ((r + c) & 1) ? base : 255 - base; break;                    /* checker        */
+                }
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+                p[r][c] = v - 128;
+            }
+        double A = 0;
+        float x[8][8];
+        for (int r = 0; r < 8; ++r)
+            for (int c = 0; c < 8; ++c) { x[r][c] = (float)p[r][c]; A += abs(p[r][c]); }
+        for (int r = 0; r < 8; ++r) dct8(&x[r][0], &x[r][1], &x[r][2], &x[r][3], &x[r][4], &x[r][5], &x[r][6], &x[r][7]);
+        for (int c = 0; c < 8; ++c) dct8(&x[0][c], &x[1][c], &x[2][c], &x[3][c], &x[4][c], &x[5][c], &x[6][c], &x[7][c]);
+        if (A == 0) continue;
+        for (int u = 0; u < 8; ++u)
+            for (int v = 0; v < 8; ++v) {
+                float acc = 0.0f;                       /* reference order, natural_c/src/core/dct.c:70-86 */
+                for (int r = 0; r < 8; ++r)
+                    for (int c = 0; c < 8; ++c) {
+                        float t = (float)p[r][c];
+                        t = t * k_cos[r][u];
+                        t = t * k_cos[c][v];
+                        acc = acc + t;
+                    }
+                const double err = fabs((double)acc - g[u] * g[v] * (double)x[u][v]) / A;
+                if (err > worst) worst = err;
+            }
+    }
+    printf("%.6e\n", worst);
+    return 0;
+}

@@ -1,0 +1,34 @@
+"""The fused kernel decides each quantized coefficient from a fast butterfly DCT only when the
+reference's own sum provably rounds to the same integer: |s_ref - g*T| <= kGamma * sum|p| with
+kGamma = 1e-5 (derivation in DESIGN.md).  This CPU test measures the actual ratio with a C
+emulation of the device butterfly (same operation order, fmaf) against the reference-order sum
+over several input families; the analytic bound must hold with a wide margin."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_guard_band_margin(tmp_path):
+    exe = str(tmp_path / "guard_band_check")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", exe,
+                    os.path.join(ROOT, "tests", "native", "guard_band_check.c"), "-lm"], check=True)
+    worst = float(subprocess.run([exe, "150000", "11"], check=True, capture_output=True, text=True).stdout)
+    cuh = open(os.path.join(ROOT, "jpeg_image_compression_b200", "csrc", "common.cuh")).read()
+    gamma = float(re.search(r"kGamma\s*=\s*([0-9.eE+-]+)f", cuh).group(1))
+    assert 0 < worst < gamma / 5, (worst, gamma)
+
+
+def test_emulated_butterfly_matches_device_source():
+    """The C emulation and the CUDA butterfly must be the same code (constants and op order)."""
+    dev = open(os.path.join(ROOT, "jpeg_image_compression_b200", "csrc", "fused_block.cuh")).read()
+    emu = open(os.path.join(ROOT, "tests", "native", "guard_band_check.c")).read()
+
+    def body(text):
+        m = re.search(r"x1 = fmaf\(b3, C7.*?x7 = fmaf\([^;]*;", text.replace("*x", "x"), re.S)
+        return re.sub(r"\s+", "", m.group(0))
+    assert body(dev) == body(emu)
+    for const in ("0.98078528040323044913f", "0.83146961230254523708f", "0.55557023301960222474f",
+                  "0.19509032201612826785f", "0.41421356237309504880f"):
+        assert const in dev and const in emu
