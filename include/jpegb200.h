@@ -192,8 +192,8 @@ typedef struct {
 int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out);
 
 /* Per-kernel device time: with profiling on, every kernel launch is bracketed by cudaEvents
- * on the launching stream.  kernel ids: 0 fused block kernel, 1 bit-offset scan, 2 bit pack,
- * 3 byte stuffing, 4 image layout, 5 shared-word clear.  Synchronises the device. */
+ * on the launching stream.  kernel ids: 0 fused block kernel (K1), 1 scan+pack+stuff (K2),
+ * 2 batch layout, 3 batch compaction.  Synchronises the device. */
 int jpegb200_encoder_set_profiling(jpegb200_encoder *enc, int on);
 int jpegb200_encoder_kernel_times(jpegb200_encoder *enc, double ms_total[8], uint64_t calls[8], int reset);
 
@@ -211,19 +211,21 @@ int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, 
 int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks);
 
 /* ---- MCU-row stripes of one image across several GPUs ----------------------
- * Rank r owns block rows [row0, row0+rows) of an image; d_rgb points at the stripe's
- * first pixel row, stripe_height = pixel rows present in the stripe (the last stripe
- * carries the image's ragged bottom).  Three phases with two tiny exchanges between
- * them (done by the caller over NCCL):
+ * Rank r owns block rows [row0, row0+rows) of an image.  d_rgb points at the stripe's first
+ * pixel row; stripe_height = pixel rows of the stripe (a multiple of 8 except for the image's
+ * last stripe, which carries the ragged bottom); halo_rows = pixel rows of the NEXT stripe's
+ * first block row that follow in the same buffer (min(8, rows left); 0 for the last stripe).
+ * The halo lets a rank finish the byte its stream ends in without receiving bits from its
+ * neighbour.  Two phases with one tiny exchange between them (done by the caller over NCCL;
+ * see INTEGRATION.md and jpeg_image_compression_b200/stripes.py):
  *
- *   analyze : block kernel + local bit lengths with DC predictor 0
- *             -> {first_dc, last_dc, bits_pred0}
- *   pack    : given the true predictor (previous stripe's last_dc) and the stripe's
- *             global bit offset, pack at the true global bit phase
- *             -> {head_byte: bits this stripe contributes to a byte that starts in an
- *                 earlier stripe, byte_first, byte_last}
- *   finish  : given the OR of later stripes' head bits for this stripe's last owned
- *             byte, byte-stuff the owned byte range -> stuffed bytes (device)      */
+ *   analyze : fused block kernel over the stripe (+ halo) -> {first_dc, last_dc, bits_pred0}
+ *             bits_pred0 = the stripe's bit count if its first block were predicted from DC 0
+ *   -- all-gather the summaries: every rank derives each stripe's true predictor (previous
+ *      stripe's last_dc), true bit count and therefore its global bit offset --
+ *   encode  : scan + pack + stuff at the true global bit phase.  The stripe emits exactly the
+ *             stuffed bytes whose first bit lies inside its bit range; the concatenation of all
+ *             ranks' bytes is the image's scan, byte-identical to the single-GPU encode.     */
 typedef struct {
     int16_t  first_dc;
     int16_t  last_dc;
@@ -231,21 +233,11 @@ typedef struct {
     uint64_t bits_pred0;
 } jpegb200_stripe_summary;
 
-typedef struct {
-    uint64_t bit_begin;             /* global bit offset of the stripe's first bit */
-    uint64_t bit_end;               /* one past its last bit                        */
-    uint32_t head_byte;             /* stripe's contribution to byte bit_begin/8    */
-    uint32_t tail_byte;             /* stripe's contribution to byte (bit_end-1)/8  */
-} jpegb200_stripe_packed;
-
-int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int width,
-                            int stripe_height, jpegb200_stripe_summary *host_out,
-                            void *cuda_stream);
-int jpegb200_stripe_pack(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin,
-                         jpegb200_stripe_packed *host_out, void *cuda_stream);
-int jpegb200_stripe_finish(jpegb200_encoder *enc, uint32_t or_into_last_byte, int owns_first_byte,
-                           int is_last_stripe, uint8_t *d_scan, uint64_t scan_capacity,
-                           uint64_t *host_scan_bytes, void *cuda_stream);
+int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
+                            int halo_rows, jpegb200_stripe_summary *host_out, void *cuda_stream);
+int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin,
+                           uint8_t *d_scan, uint64_t scan_capacity, uint64_t *host_scan_bytes,
+                           void *cuda_stream);
 
 /* Synthetic workload generator on the device:
  * fills count images of w x h RGB, image i uses seed0 + i. */

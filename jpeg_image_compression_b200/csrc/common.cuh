@@ -112,4 +112,50 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *state, in
     return excl;
 }
 
+// CTA-wide variant: all 256 threads of the CTA take part, 256 predecessors per round (a few
+// hundred tiles resolve in one or two rounds instead of a dozen).  Every thread returns the
+// exclusive prefix.  s_scratch: 24 words of shared memory.  Must be called by the whole CTA.
+__device__ __forceinline__ uint64_t lookback_exclusive_cta(const uint64_t *state, int tile, uint32_t *err,
+                                                           uint64_t *s_scratch)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    uint32_t *s_first = reinterpret_cast<uint32_t *>(s_scratch);      // [8]  lane of the nearest PREFIX per warp (32: none)
+    uint64_t *s_sum = s_scratch + 4;                                  // [8]  per-warp sums
+    uint64_t excl = 0;
+    int base = tile - 1;
+    while (base >= 0) {
+        const int j = base - tid;
+        uint64_t v = 0;
+        uint32_t status = LB_PREFIX;                                  // virtual tile before tile 0: prefix 0
+        if (j >= 0) {
+            int spins = 0;
+            for (;;) {
+                v = ld_volatile_u64(state + j);
+                status = (uint32_t)(v >> LB_STATUS_SHIFT) & 3u;
+                if (status != 0) break;
+                if (++spins > (1 << 22)) { atomicOr(err, ERRBIT_LOOKBACK); status = LB_PREFIX; v = 0; break; }
+                __nanosleep(20);
+            }
+            v &= LB_VALUE_MASK;
+        }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, status == LB_PREFIX);
+        if (lane == 0) s_first[warp] = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
+        __syncthreads();
+        int wstar = nwarp;                                            // nearest warp holding a PREFIX
+        for (int w = nwarp - 1; w >= 0; --w)
+            if (s_first[w] < 32u) wstar = w;
+        const bool take = warp < wstar || (warp == wstar && (uint32_t)lane <= s_first[wstar]);
+        uint64_t c = take ? v : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) s_sum[warp] = c;
+        __syncthreads();
+        for (int w = 0; w < nwarp; ++w) excl += s_sum[w];
+        __syncthreads();
+        if (wstar < nwarp) break;
+        base -= (int)blockDim.x;
+    }
+    return excl;
+}
+
 }  // namespace jb

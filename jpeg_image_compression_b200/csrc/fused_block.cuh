@@ -8,7 +8,7 @@
 // Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels,
 // 6 KB of RGB).  One warp owns a strip:
 //   1. 16-byte cp.async (LDGSTS, L2-only) of the 8 pixel rows into shared memory, at
-//      the rows' natural 16-byte phase (any width / base alignment: one generic path);
+//      the rows' natural 16-byte phase (any width / base alignment);
 //   2. cooperative luma pass: 4 pixels per lane-step (funnel-shift realign, PRMT, DP4A),
 //      bytes written to a 256 x 8 Y tile;
 //   3. the next strip's cp.async is issued (the raw tile is free again) so its HBM
@@ -32,6 +32,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "scan_pack.cuh"
 
 namespace jb {
 
@@ -42,47 +43,63 @@ constexpr int RAW_BYTES = 8 * RAW_PITCH;             // 6272
 constexpr int Y_PITCH = 256;
 constexpr int Y_BYTES = 8 * Y_PITCH;                 // 2048
 constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES;    // 8320
-constexpr int ACLUT_ROWS = 63;                       // run 0..62
-constexpr int ACLUT_BYTES = 16384;                   // 63*256 rounded up
+constexpr int ACLUT_BYTES = 16400;                   // 63 rows x 260 bytes + EOB length, then 16 DC lengths
 constexpr int K1_SMEM = ACLUT_BYTES + K1_WARPS * K1_WARP_SMEM;   // 82944
 
-struct StripPos {
-    uint64_t img;
-    int brow, sx;
+// Everything a warp needs to know about one strip; computed once per strip (32-bit math).
+struct StripCtx {
+    const uint8_t *row0;     // first byte of the strip's first pixel row
+    uint64_t block0;         // global index of the strip's first block
+    uint32_t pitch;          // bytes per pixel row (3 * width)
+    int rmax;                // last real pixel row of the strip, relative (rows beyond replicate it)
+    int npx;                 // real pixels per row in the strip (<= 256)
+    int vb;                  // 8x8 blocks in the strip (<= 32)
+    uint32_t mispack;        // 16-byte phase of each of the 8 row pointers, 4 bits per row
 };
 
-__device__ __forceinline__ StripPos strip_pos(const Geom &g, uint64_t s)
+__device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
 {
-    const uint64_t per_image = (uint64_t)g.bh * (uint64_t)g.spr;
-    StripPos p;
-    p.img = s / per_image;
-    const uint32_t rem = (uint32_t)(s - p.img * per_image);
-    p.brow = (int)(rem / (uint32_t)g.spr);
-    p.sx = (int)(rem - (uint32_t)p.brow * (uint32_t)g.spr);
-    return p;
+    const uint32_t per_image = (uint32_t)g.bh * (uint32_t)g.spr;
+    const uint32_t img = s / per_image;
+    const uint32_t rem = s - img * per_image;
+    const uint32_t brow = rem / (uint32_t)g.spr;
+    const uint32_t sx = rem - brow * (uint32_t)g.spr;
+    StripCtx c;
+    c.pitch = 3u * (uint32_t)g.w;
+    c.row0 = g.rgb + (uint64_t)img * g.image_stride + (uint64_t)(brow * 8u) * c.pitch + (uint64_t)sx * 768u;
+    c.block0 = (uint64_t)img * g.blocks_per_image + (uint64_t)brow * (uint32_t)g.bw + sx * 32u;
+    c.rmax = min(7, g.h - 1 - (int)(brow * 8u));                          // converter.c:31
+    c.npx = min(256, g.w - (int)(sx * 256u));
+    c.vb = min(32, g.bw - (int)(sx * 32u));
+    const uint32_t m0 = (uint32_t)((uintptr_t)c.row0 & 15u), step = c.pitch & 15u;
+    c.mispack = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) c.mispack |= ((m0 + (uint32_t)min(r, c.rmax) * step) & 15u) << (4 * r);
+    return c;
 }
 
-__device__ __forceinline__ const uint8_t *strip_row_ptr(const Geom &g, const StripPos &p, int r)
+// stage the strip's 8 pixel rows (cp.async, 16 B per lane-step, at most two steps per row)
+__device__ __forceinline__ void strip_issue_loads(const StripCtx &c, uint8_t *raw, int lane)
 {
-    int y = p.brow * 8 + r;
-    y = y < g.h ? y : g.h - 1;                                            // converter.c:31
-    return g.rgb + p.img * g.image_stride + ((uint64_t)y * (uint64_t)g.w + (uint64_t)p.sx * 256u) * 3u;
-}
-
-// stage the strip's 8 pixel rows (cp.async, 16 B per lane-step)
-__device__ __forceinline__ void strip_issue_loads(const Geom &g, uint64_t s, uint8_t *raw, int lane)
-{
-    const StripPos p = strip_pos(g, s);
-    const int npx = min(256, g.w - p.sx * 256);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const uint8_t *src = strip_row_ptr(g, p, r);
-        const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
-        const uint8_t *a0 = src - mis;
-        const int nch = (int)((mis + 3u * (uint32_t)npx + 15u) >> 4);
-        for (int c = lane; c < nch; c += 32) cp_async16(raw + r * RAW_PITCH + c * 16, a0 + c * 16);
+        const uint32_t mis = (c.mispack >> (4 * r)) & 15u;
+        const uint8_t *a0 = c.row0 + (uint64_t)((uint32_t)min(r, c.rmax) * c.pitch) - mis;
+        const int nch = (int)((mis + 3u * (uint32_t)c.npx + 15u) >> 4);    // <= 49
+        if (lane < nch) cp_async16(raw + r * RAW_PITCH + lane * 16, a0 + lane * 16);
+        if (lane + 32 < nch) cp_async16(raw + r * RAW_PITCH + (lane + 32) * 16, a0 + (lane + 32) * 16);
     }
     cp_async_commit();
+}
+
+// luma of 4 consecutive pixels held in 3 words: Y = (77R + 150G + 29B) >> 8  (converter.c:51)
+__device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const uint32_t y0 = __dp4a(w0, 0x001D964Du, 0u);
+    const uint32_t y1 = __dp4a(__byte_perm(w0, w1, 0x0543u), 0x001D964Du, 0u);
+    const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), 0x001D964Du, 0u);
+    const uint32_t y3 = __dp4a(w2, 0x1D964D00u, 0u);
+    return __byte_perm(__byte_perm(y0, y1, 0x0051u), __byte_perm(y2, y3, 0x0051u), 0x5410u);
 }
 
 // Reference-order evaluation of ONE quantized coefficient (dct.c:65-93,
@@ -137,80 +154,92 @@ __device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 2)
-k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blockinfo,
-               const uint8_t *__restrict__ aclut_g, unsigned long long *__restrict__ flagged_counter,
-               const int exact_mode, uint64_t *__restrict__ lookback_state, const uint64_t lookback_words)
+k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blkinfo,
+               StripRec *__restrict__ strips, const uint8_t *__restrict__ tables,
+               unsigned long long *__restrict__ flagged_counter, const int exact_mode,
+               uint64_t *__restrict__ lookback_state, const uint64_t lookback_words)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *aclut = smem;
+    const uint8_t *s_dclen = smem + TBL_DC_LEN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *raw = smem + ACLUT_BYTES + warp * K1_WARP_SMEM;
     uint8_t *ybuf = raw + RAW_BYTES;
 
-    for (int i = threadIdx.x; i < ACLUT_BYTES / 16; i += K1_THREADS)
-        reinterpret_cast<uint4 *>(aclut)[i] = reinterpret_cast<const uint4 *>(aclut_g)[i];
+    const uint32_t nwarps = gridDim.x * K1_WARPS;
+    uint32_t s = blockIdx.x * K1_WARPS + warp;
+    const uint32_t total = (uint32_t)g.total_strips;
+    StripCtx cur;
+    if (s < total) {
+        cur = strip_ctx(g, s);
+        strip_issue_loads(cur, raw, lane);                       // first strip's pixels are in flight ...
+    }
+    for (int i = threadIdx.x; i < ACLUT_BYTES / 16; i += K1_THREADS)   // ... while the bit-cost table is staged
+        cp_async16(aclut + i * 16, tables + TBL_ACLUT + i * 16);
+    cp_async_commit();
     // reset the decoupled look-back state of the scan (K2) and stuffing (K4) kernels that
     // follow in the stream: keeps a whole encode at four launches and CUDA-graph replayable
     for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;
          i += (uint64_t)gridDim.x * K1_THREADS)
         lookback_state[i] = 0;
+    cp_async_wait_all();
     __syncthreads();
 
-    const uint64_t nwarps = (uint64_t)gridDim.x * K1_WARPS;
-    uint64_t s = (uint64_t)blockIdx.x * K1_WARPS + warp;
-    if (s < g.total_strips) strip_issue_loads(g, s, raw, lane);
     uint32_t nflag = 0;
+    const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
 
-    for (; s < g.total_strips; s += nwarps) {
-        const StripPos p = strip_pos(g, s);
-        const int npx = min(256, g.w - p.sx * 256);               // real pixels in the strip
-        const int vb = min(32, g.bw - p.sx * 32);                 // blocks in the strip
-        uint32_t mispack = 0;                                     // 16-byte phase of each row
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            mispack |= (uint32_t)((uintptr_t)strip_row_ptr(g, p, r) & 15u) << (4 * r);
-
+    for (; s < total; s += nwarps) {
         cp_async_wait_all();
         __syncwarp();
 
-        // ---- luma pass: Y = (77R + 150G + 29B) >> 8  (converter.c:51) --------------
-        const int ngroups = (npx + 3) >> 2;
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int item = lane + 32 * i;
-            const int r = item >> 6, gc = item & 63;
-            if (gc < ngroups) {
-                const uint32_t mis = (mispack >> (4 * r)) & 15u;
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH) + (mis >> 2) + 3 * gc;
-                const uint32_t sh = (mis & 3u) * 8u;
-                const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
-                const uint32_t w0 = __funnelshift_r(q0, q1, sh);
-                const uint32_t w1 = __funnelshift_r(q1, q2, sh);
-                const uint32_t w2 = __funnelshift_r(q2, q3, sh);
-                const uint32_t y0 = __dp4a(w0, 0x001D964Du, 0u);
-                const uint32_t y1 = __dp4a(__byte_perm(w0, w1, 0x0543u), 0x001D964Du, 0u);
-                const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), 0x001D964Du, 0u);
-                const uint32_t y3 = __dp4a(w2, 0x1D964D00u, 0u);
-                const uint32_t lo = __byte_perm(y0, y1, 0x0051u), hi = __byte_perm(y2, y3, 0x0051u);
-                reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] = __byte_perm(lo, hi, 0x5410u);
+        // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
+        if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
+            // full strip, word-aligned rows: 3 LDS + DP4A/PRMT per 4 pixels, fully unrolled
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
+                uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
+                yo[lane] = luma4(rw[0], rw[1], rw[2]);
+                yo[lane + 32] = luma4(rw[96], rw[97], rw[98]);
+            }
+        } else {
+            // any width / any base alignment: funnel-shift the row to word alignment
+            const int ngroups = (cur.npx + 3) >> 2;
+#pragma unroll 1
+            for (int item = lane; item < 512; item += 32) {
+                const int r = item >> 6, gc = item & 63;
+                if (gc < ngroups) {
+                    const uint32_t mis = (cur.mispack >> (4 * r)) & 15u;
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH) + (mis >> 2) + 3 * gc;
+                    const uint32_t sh = (mis & 3u) * 8u;
+                    const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
+                    reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] =
+                        luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh));
+                }
             }
         }
         __syncwarp();
 
         // raw tile is free: prefetch the next strip while this one is transformed
-        if (s + nwarps < g.total_strips) strip_issue_loads(g, s + nwarps, raw, lane);
+        const StripCtx me = cur;
+        if (s + nwarps < total) {
+            cur = strip_ctx(g, s + nwarps);
+            strip_issue_loads(cur, raw, lane);
+        }
 
         // right-edge replication inside the last real block (converter.c:36)
-        const int padpx = vb * 8 - npx;
+        const int padpx = me.vb * 8 - me.npx;
         if (padpx > 0) {
             if (lane < padpx) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) ybuf[r * Y_PITCH + npx + lane] = ybuf[r * Y_PITCH + npx - 1];
+                for (int r = 0; r < 8; ++r) ybuf[r * Y_PITCH + me.npx + lane] = ybuf[r * Y_PITCH + me.npx - 1];
             }
             __syncwarp();
         }
 
-        if (lane < vb) {
+        uint32_t my_bits = 0, my_last = 0;                     // this lane's block: bit cost, last non-zero AC index
+        int my_dc = 0;
+        if (lane < me.vb) {
             const uint8_t *yblk = ybuf + lane * 8;
             float x[8][8];
             uint32_t absdev = 0;                                   // A = sum |Y - 128|
@@ -262,7 +291,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 const uint32_t h = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040u), __byte_perm(hb[2], hb[3], 0x0040u), 0x5410u);
                 const uint32_t l = __byte_perm(__byte_perm(lb[0], lb[1], 0x0040u), __byte_perm(lb[2], lb[3], 0x0040u), 0x5410u);
                 zw[w] = h;
-                xw[w] = exact_mode ? 0x01010101u : (h ^ l);
+                xw[w] = (h ^ l) | xforce;
             }
 
             // DC: exact integer sum in both formulations; reference operation sequence
@@ -277,41 +306,64 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             uint32_t anyx = 0;
 #pragma unroll
             for (int w = 0; w < 16; ++w) anyx |= xw[w];
-            if (anyx) {                                            // rare: reference-order re-evaluation
+            if (anyx) {
+                // rare (about 1 block in 200): the bracket straddles a rounding boundary for some
+                // coefficient(s); re-evaluate exactly those in the reference's operation order
+                uint64_t fm = 0;
 #pragma unroll
                 for (int w = 0; w < 16; ++w) {
-                    if (xw[w]) {
+                    const uint32_t t = xw[w];
+                    const uint32_t nib = (t & 0xFFu ? 1u : 0u) | (t & 0xFF00u ? 2u : 0u) | (t & 0xFF0000u ? 4u : 0u) | (t & 0xFF000000u ? 8u : 0u);
+                    fm |= (uint64_t)nib << (4 * w);
+                }
+#pragma unroll 1
+                while (fm) {
+                    const int k = __ffsll((long long)fm) - 1;
+                    fm &= fm - 1;
+                    const int pos = c_zigzag[k];
+                    const uint32_t q = (uint32_t)exact_quantized(yblk, pos >> 3, pos & 7) & 0xFFu;
+                    const uint32_t sh = 8u * (uint32_t)(k & 3), keep = ~(0xFFu << sh), ins = q << sh;
+                    const int kw = k >> 2;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if ((xw[w] >> (8 * j)) & 0xFFu) {
-                                const int pos = c_zigzag[4 * w + j];
-                                const int q = exact_quantized(yblk, pos >> 3, pos & 7);
-                                zw[w] = (zw[w] & ~(0xFFu << (8 * j))) | (((uint32_t)q & 0xFFu) << (8 * j));
-                                ++nflag;
-                            }
-                        }
-                    }
+                    for (int w = 0; w < 16; ++w)
+                        if (w == kw) zw[w] = (zw[w] & keep) | ins;
+                    ++nflag;
                 }
             }
 
             // AC bit cost: code length + amplitude bits per non-zero coefficient, ZRLs, EOB
-            uint32_t bits = 0, lastk256 = 0;
+            uint32_t bits = 0, lastk = 0;                          // lastk = ACLUT_STRIDE * (index of the last non-zero)
 #pragma unroll
             for (int k = 1; k < 64; ++k) {
                 const uint32_t byte = __byte_perm(zw[k >> 2], 0u, 0x4440u + (uint32_t)(k & 3));
-                bits += aclut[byte + (uint32_t)((k - 1) * 256) - lastk256];
-                if (byte != 0) lastk256 = (uint32_t)(k * 256);
+                bits += aclut[byte + (uint32_t)((k - 1) * ACLUT_STRIDE) - lastk];
+                if (byte != 0) lastk = (uint32_t)(k * ACLUT_STRIDE);
             }
-            if (lastk256 != 63u * 256u) bits += (c_ac_code[0] & 0xFFu);   // EOB (rle.c:121-123)
+            my_last = (lastk * 253u) >> 16;                        // lastk / 260 for lastk <= 63*260
+            if (my_last != 63u) bits += aclut[ACLUT_ROWS * ACLUT_STRIDE];   // EOB code length (rle.c:121-123)
+            my_bits = bits;
+            my_dc = (int)(int8_t)(zw[0] & 0xFFu);
 
-            const uint64_t b = p.img * g.blocks_per_image + (uint64_t)p.brow * (uint64_t)g.bw + (uint64_t)(p.sx * 32 + lane);
-            uint4 *dst = reinterpret_cast<uint4 *>(coef + b * 64);
+            uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 64);
             dst[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
             dst[1] = make_uint4(zw[4], zw[5], zw[6], zw[7]);
             dst[2] = make_uint4(zw[8], zw[9], zw[10], zw[11]);
             dst[3] = make_uint4(zw[12], zw[13], zw[14], zw[15]);
-            const int dc = (int)(int8_t)(zw[0] & 0xFFu);
-            blockinfo[b] = (bits << 16) | ((uint32_t)dc & 0xFFFFu);
+        }
+        // DC-difference cost inside the strip (rle.c:68-76); the strip's first block is charged by K2,
+        // which knows the previous strip's last DC.  Then the strip-local exclusive bit offsets.
+        {
+            const int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+            if (lane > 0 && lane < me.vb) my_bits += s_dclen[magnitude_class(my_dc - prev_dc)];
+            uint32_t incl = my_bits;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const int first_dc = __shfl_sync(0xffffffffu, my_dc, 0);
+            if (lane < me.vb) blkinfo[me.block0 + (uint32_t)lane] = blk_pack(incl - my_bits, my_last);
+            if (lane == me.vb - 1) strips[s] = StripRec{incl, (int16_t)first_dc, (int16_t)my_dc};
         }
         __syncwarp();
     }

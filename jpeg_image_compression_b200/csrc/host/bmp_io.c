@@ -69,7 +69,8 @@ BMPImage *loadBMPImage(const char *filename)
     }
     const size_t w = (size_t)(img->width > 0 ? img->width : 0), h = (size_t)img->height;
     const size_t pitch = (w * 3u + 3u) & ~(size_t)3u;    /* bmp_handler.c:75 */
-    img->data = (uint8_t *)malloc(w * h * 3u ? w * h * 3u : 1u);   /* 64-bit sizes: no overflow above 715 Mpx */
+    const size_t nbytes = w * h * 3u;                    /* 64-bit sizes: no overflow above 715 Mpx */
+    img->data = (uint8_t *)malloc(nbytes > 0 ? nbytes : 1u);
     if (!img->data) {
         fprintf(stderr, "Error: Memory allocation failed for pixel data.\n");
         free(img);

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "scan_pack.cuh"
 #include "entropy.cuh"
 #include "fused_block.cuh"
 #include "stages.cuh"
@@ -73,7 +74,7 @@ struct HostTables {
     float ref_scale[64], quant_f[64], rk[64];
     uint8_t dc_len[16];
     uint32_t dc_code[16], ac_code[256];
-    std::vector<uint8_t> aclut;      // [63][256] bit cost of (run, int8 value)
+    std::vector<uint8_t> block;      // device table block, TBL_* layout (scan_pack.cuh)
 };
 
 static int bit_length(int v) { int a = v < 0 ? -v : v, n = 0; while (a) { ++n; a >>= 1; } return n; }
@@ -99,16 +100,20 @@ static void build_tables(HostTables &t)
         t.dc_code[i] = ((uint32_t)dc[i].code << 8) | dc[i].len;
     }
     for (int i = 0; i < 256; ++i) t.ac_code[i] = ((uint32_t)ac[i].code << 8) | ac[i].len;
-    t.aclut.assign(ACLUT_BYTES, 0);
+    t.block.assign(TBL_BYTES, 0);
+    // bit cost of an AC coefficient with int8 value b after `run` zeros: ZRLs + code + amplitude bits
     for (int run = 0; run < ACLUT_ROWS; ++run) {
         for (int b = 1; b < 256; ++b) {
-            const int v = (int)(int8_t)b;
-            const int sz = bit_length(v);
+            const int sz = bit_length((int)(int8_t)b);
             if (sz > 10) continue;
-            const int cost = (run >> 4) * ac[0xF0].len + ac[((run & 15) << 4) | sz].len + sz;
-            t.aclut[run * 256 + b] = (uint8_t)cost;
+            t.block[TBL_ACLUT + run * ACLUT_STRIDE + b] =
+                (uint8_t)((run >> 4) * ac[0xF0].len + ac[((run & 15) << 4) | sz].len + sz);
         }
     }
+    t.block[TBL_ACLUT + ACLUT_ROWS * ACLUT_STRIDE] = ac[0x00].len;          // EOB
+    memcpy(&t.block[TBL_AC_CODE], t.ac_code, sizeof(t.ac_code));
+    memcpy(&t.block[TBL_DC_CODE], t.dc_code, sizeof(t.dc_code));
+    memcpy(&t.block[TBL_DC_LEN], t.dc_len, sizeof(t.dc_len));
 }
 
 // ---- encoder handle ---------------------------------------------------------------
@@ -142,13 +147,13 @@ struct jpegb200_encoder {
     int sm_count = 148;
     int dct_mode = 0;
     int bytes_per_block = 24;
-    jb::DeviceBuffer coef, blockinfo, blockoff, tilebase, lookback, image_bits, image_base, packed, image_ff, aclut,
-        misc, host_in, host_scan;
+    jb::HostTables tables;
+    jb::DeviceBuffer coef, blkinfo, strips, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan;
     // last launch
-    jb::EntropyArgs args{};
+    jb::PackArgs args{};
     jb::Geom geom{};
     uint64_t lookback_words = 0;
-    uint64_t total_blocks = 0;
+    uint64_t total_blocks = 0;      // blocks K1 produced (all images, incl. stripe halo)
     uint64_t launches = 0;
     bool stripe_ready = false;
     // optional per-kernel timing (cudaEvents on the launching stream)
@@ -166,7 +171,7 @@ static bool g_tables_uploaded[64] = {false};
 
 static int upload_tables(jpegb200_encoder *enc)
 {
-    HostTables t;
+    HostTables &t = enc->tables;
     build_tables(t);
     {
         std::lock_guard<std::mutex> lock(g_tables_mutex);
@@ -180,13 +185,13 @@ static int upload_tables(jpegb200_encoder *enc)
             JB_CUDA(cudaMemcpyToSymbol(c_dc_code, t.dc_code, sizeof(t.dc_code)));
             JB_CUDA(cudaMemcpyToSymbol(c_ac_code, t.ac_code, sizeof(t.ac_code)));
             JB_CUDA(cudaFuncSetAttribute(k_fused_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_WORDS * 4));
+            JB_CUDA(cudaFuncSetAttribute(k_scan_pack_stuff, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
             g_tables_uploaded[enc->device & 63] = true;
         }
     }
-    int rc = enc->aclut.reserve(ACLUT_BYTES);
+    int rc = enc->dtables.reserve(TBL_BYTES);
     if (rc) return rc;
-    JB_CUDA(cudaMemcpy(enc->aclut.ptr, t.aclut.data(), ACLUT_BYTES, cudaMemcpyHostToDevice));
+    JB_CUDA(cudaMemcpy(enc->dtables.ptr, t.block.data(), TBL_BYTES, cudaMemcpyHostToDevice));
     rc = enc->misc.reserve(256);
     if (rc) return rc;
     JB_CUDA(cudaMemset(enc->misc.ptr, 0, 256));
@@ -204,66 +209,73 @@ static uint64_t *misc_offsets(jpegb200_encoder *e)
     return reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(e->misc.ptr) + 16);
 }
 
-// Fill geometry + workspace for `count` images of w x h.
-static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, int count, uint64_t stride)
+// Fill geometry + workspace for `count` images of w x h.  halo_rows > 0 (stripes): the last
+// halo_rows pixel rows belong to the NEXT stripe; K1 transforms them (one extra block row) so
+// that K2 can complete this stripe's last byte, but they are not part of this stripe's stream.
+static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, int count, uint64_t stride, int halo_rows)
 {
-    if (!enc || !d_rgb || w <= 0 || h <= 0 || count <= 0) {
+    if (!enc || !d_rgb || w <= 0 || h <= 0 || count <= 0 || halo_rows < 0 || halo_rows > 8 || (halo_rows && (h & 7))) {
         g_last_error = "bad argument";
         return JPEGB200_ERR_ARG;
     }
-    if (stride == 0) stride = (uint64_t)w * (uint64_t)h * 3u;
+    if (stride == 0) stride = (uint64_t)w * (uint64_t)(h + halo_rows) * 3u;
     JB_CUDA(cudaSetDevice(enc->device));
     Geom &g = enc->geom;
     g.rgb = d_rgb;
     g.image_stride = stride;
     g.w = w;
-    g.h = h;
+    g.h = h + halo_rows;
     g.bw = (w + 7) / 8;
-    g.bh = (h + 7) / 8;
+    g.bh = (h + 7) / 8 + (halo_rows ? 1 : 0);
     g.spr = (g.bw + 31) / 32;
     g.count = count;
     g.blocks_per_image = (uint64_t)g.bw * (uint64_t)g.bh;
     g.total_strips = (uint64_t)g.spr * (uint64_t)g.bh * (uint64_t)count;
-    const uint64_t nb = g.blocks_per_image, tb = nb * (uint64_t)count;
+    if (g.total_strips >= (1ull << 31)) {
+        g_last_error = "launch too large: split the batch (strip index is 32-bit)";
+        return JPEGB200_ERR_ARG;
+    }
+    const uint64_t nb_avail = g.blocks_per_image, tb = nb_avail * (uint64_t)count;
+    const uint32_t strips_avail = (uint32_t)g.spr * (uint32_t)g.bh;
+    const uint32_t strips_owned = (uint32_t)g.spr * (uint32_t)((h + 7) / 8);
+    const uint64_t nb_owned = (uint64_t)g.bw * (uint64_t)((h + 7) / 8);
     enc->total_blocks = tb;
-    const int tiles = (int)((nb + K2_TILE - 1) / K2_TILE);
-    const uint64_t packed_per_image = ((nb * (uint64_t)enc->bytes_per_block + 15) & ~15ull) + 32;
-    const int chunks_cap = (int)((packed_per_image + K4_CHUNK - 1) / K4_CHUNK);
+    const int tiles = (int)((strips_owned + K2_WARPS - 1) / K2_WARPS);
     int rc = 0;
     if ((rc = enc->coef.reserve(tb * 64))) return rc;
-    if ((rc = enc->blockinfo.reserve(tb * 4))) return rc;
-    if ((rc = enc->blockoff.reserve(tb * 4))) return rc;
-    if ((rc = enc->tilebase.reserve((uint64_t)tiles * count * 8))) return rc;
-    // look-back state of K2 (one word per scan tile) and K4 (one word per 4 KiB chunk), contiguous so
-    // that K1's prologue clears both
-    enc->lookback_words = (uint64_t)tiles * count + (uint64_t)chunks_cap * count;
+    if ((rc = enc->blkinfo.reserve(tb * 4))) return rc;
+    if ((rc = enc->strips.reserve(g.total_strips * sizeof(StripRec)))) return rc;
+    // look-back state of K2: one word per tile for the bit offsets, one for the stuffed-zero counts;
+    // contiguous, cleared by K1's prologue
+    enc->lookback_words = 2ull * (uint64_t)tiles * (uint64_t)count;
     if ((rc = enc->lookback.reserve(enc->lookback_words * 8))) return rc;
     if ((rc = enc->image_bits.reserve((uint64_t)count * 8))) return rc;
-    if ((rc = enc->image_base.reserve((uint64_t)count * 8))) return rc;
-    if ((rc = enc->image_ff.reserve((uint64_t)count * 8))) return rc;
-    if ((rc = enc->packed.reserve(packed_per_image * (uint64_t)count + 64))) return rc;
+    if ((rc = enc->image_bytes.reserve((uint64_t)count * 8))) return rc;
+    // batch: every image is stuffed into its own slot, then compacted; stuffed size <= 2 x packed size
+    const uint64_t slot = ((2 * (nb_owned * (uint64_t)enc->bytes_per_block + 64)) + 15) & ~15ull;
+    if (count > 1 && (rc = enc->slots.reserve(slot * (uint64_t)count + 64))) return rc;
 
-    EntropyArgs &a = enc->args;
+    PackArgs &a = enc->args;
+    a.tables = static_cast<const uint8_t *>(enc->dtables.ptr);
     a.coef = static_cast<const int8_t *>(enc->coef.ptr);
-    a.blockinfo = static_cast<const uint32_t *>(enc->blockinfo.ptr);
-    a.blockoff = static_cast<uint32_t *>(enc->blockoff.ptr);
-    a.tilebase = static_cast<uint64_t *>(enc->tilebase.ptr);
-    a.scan_state = static_cast<uint64_t *>(enc->lookback.ptr);
+    a.blkinfo = static_cast<const uint32_t *>(enc->blkinfo.ptr);
+    a.strips = static_cast<const StripRec *>(enc->strips.ptr);
+    a.bit_state = static_cast<uint64_t *>(enc->lookback.ptr);
+    a.ff_state = a.bit_state + (uint64_t)tiles * (uint64_t)count;
+    a.out = count > 1 ? static_cast<uint8_t *>(enc->slots.ptr) : nullptr;
+    a.out_capacity = count > 1 ? slot : 0;
+    a.out_slot = count > 1 ? slot : 0;
+    a.image_bytes = static_cast<uint64_t *>(enc->image_bytes.ptr);
     a.image_bits = static_cast<uint64_t *>(enc->image_bits.ptr);
-    a.image_base = static_cast<uint64_t *>(enc->image_base.ptr);
-    a.packed = static_cast<uint32_t *>(enc->packed.ptr);
-    a.packed_capacity = packed_per_image * (uint64_t)count;
-    a.stuff_state = static_cast<uint64_t *>(enc->lookback.ptr) + (uint64_t)tiles * count;
-    a.image_ff = static_cast<uint64_t *>(enc->image_ff.ptr);
-    a.scan = nullptr;
-    a.scan_capacity = 0;
     a.scan_offsets = nullptr;
     a.err = misc_err(enc);
-    a.nb = nb;
+    a.strips_owned = strips_owned;
+    a.strips_avail = strips_avail;
+    a.spr = (uint32_t)g.spr;
+    a.bw = (uint32_t)g.bw;
+    a.nb_avail = (uint32_t)nb_avail;
     a.tiles = tiles;
-    a.chunks_cap = chunks_cap;
     a.count = count;
-    a.epoch = 1;
     a.dc_pred0 = 0;
     a.bit_phase = 0;
     return JPEGB200_OK;
@@ -271,7 +283,7 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
 
 // ---- kernel launches (optionally bracketed by cudaEvents for per-kernel timing) -----------
 
-enum KernelId { KID_BLOCK = 0, KID_SCAN = 1, KID_PACK = 2, KID_STUFF = 3, KID_LAYOUT = 4, KID_ZERO = 5 };
+enum KernelId { KID_BLOCK = 0, KID_ENTROPY = 1, KID_LAYOUT = 2, KID_COMPACT = 3 };
 
 struct TimedLaunch {
     jpegb200_encoder *enc;
@@ -291,6 +303,7 @@ struct TimedLaunch {
     ~TimedLaunch() { if (stop) cudaEventRecord(stop, st); }
 };
 
+// K1: fused block kernel, persistent, two CTAs per SM
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
     const Geom &g = enc->geom;
@@ -299,8 +312,9 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     {
         TimedLaunch t(enc, st, KID_BLOCK);
         k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
-                                                           static_cast<uint32_t *>(enc->blockinfo.ptr),
-                                                           static_cast<const uint8_t *>(enc->aclut.ptr), misc_flagged(enc),
+                                                           static_cast<uint32_t *>(enc->blkinfo.ptr),
+                                                           static_cast<StripRec *>(enc->strips.ptr),
+                                                           static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc),
                                                            enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
                                                            enc->lookback_words);
     }
@@ -308,35 +322,13 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     return JPEGB200_OK;
 }
 
-static int launch_bit_scan(jpegb200_encoder *enc, cudaStream_t st)
+// K2: fused scan + pack + stuff, one CTA per tile of 8 strips
+static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {
-    const EntropyArgs &a = enc->args;
+    const PackArgs &a = enc->args;
     {
-        TimedLaunch t(enc, st, KID_SCAN);
-        k_bit_scan<<<dim3(a.tiles, a.count), K2_THREADS, 0, st>>>(a);
-    }
-    JB_CUDA(cudaGetLastError());
-    return JPEGB200_OK;
-}
-
-static int launch_pack(jpegb200_encoder *enc, cudaStream_t st)
-{
-    const EntropyArgs &a = enc->args;
-    const unsigned ptiles = (unsigned)((a.nb + K3_THREADS - 1) / K3_THREADS);
-    {
-        TimedLaunch t(enc, st, KID_PACK);
-        k_pack<<<dim3(ptiles, a.count), K3_THREADS, K3_SMEM_WORDS * 4, st>>>(a);
-    }
-    JB_CUDA(cudaGetLastError());
-    return JPEGB200_OK;
-}
-
-static int launch_stuff(jpegb200_encoder *enc, const StuffArgs &sa, cudaStream_t st)
-{
-    const EntropyArgs &a = enc->args;
-    {
-        TimedLaunch t(enc, st, KID_STUFF);
-        k_stuff<<<dim3(a.chunks_cap, a.count), K4_THREADS, 0, st>>>(a, sa);
+        TimedLaunch t(enc, st, KID_ENTROPY);
+        k_scan_pack_stuff<<<dim3((unsigned)a.tiles, (unsigned)a.count), K2_THREADS, K2_SMEM, st>>>(a);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -364,34 +356,26 @@ static int encode_launch(jpegb200_encoder *enc, uint8_t *d_scan, uint64_t scan_c
     int rc = 0;
     enc->launches = 0;
     enc->stripe_ready = false;
-    EntropyArgs &a = enc->args;
-    a.scan = d_scan;
-    a.scan_capacity = scan_capacity;
+    PackArgs &a = enc->args;
     a.scan_offsets = d_scan_offsets;
-    if ((rc = launch_block_kernel(enc, st))) return rc;
-    if ((rc = launch_bit_scan(enc, st))) return rc;
     if (a.count == 1) {
-        if ((rc = launch_pack(enc, st))) return rc;
-        if ((rc = launch_stuff(enc, StuffArgs{0, 0, 0}, st))) return rc;
-    } else {
+        a.out = d_scan;
+        a.out_capacity = scan_capacity;
+    }
+    if ((rc = launch_block_kernel(enc, st))) return rc;
+    if ((rc = launch_entropy(enc, st))) return rc;
+    if (a.count > 1) {
         {
             TimedLaunch t(enc, st, KID_LAYOUT);
-            k_image_layout<<<1, 1024, 0, st>>>(a, 0);
+            k_layout<<<1, 1024, 0, st>>>(a.image_bytes, d_scan_offsets, a.count, scan_capacity, a.err);
         }
-        const uint64_t ptiles = (a.nb + K3_THREADS - 1) / K3_THREADS * (uint64_t)a.count;
         {
-            TimedLaunch t(enc, st, KID_ZERO);
-            k_zero_shared_words<<<(unsigned)((ptiles + 255) / 256), 256, 0, st>>>(a);
+            TimedLaunch t(enc, st, KID_COMPACT);
+            const unsigned gx = (unsigned)std::min<uint64_t>((a.out_slot / 16 + 255) / 256, 64);
+            k_compact<<<dim3(gx, (unsigned)a.count), 256, 0, st>>>(a.out, a.out_slot, a.image_bytes, d_scan_offsets, d_scan,
+                                                                   scan_capacity);
         }
         JB_CUDA(cudaGetLastError());
-        if ((rc = launch_pack(enc, st))) return rc;
-        if ((rc = launch_stuff(enc, StuffArgs{1, 0, 0}, st))) return rc;
-        {
-            TimedLaunch t(enc, st, KID_LAYOUT);
-            k_image_layout<<<1, 1024, 0, st>>>(a, 1);
-        }
-        JB_CUDA(cudaGetLastError());
-        if ((rc = launch_stuff(enc, StuffArgs{2, 0, 0}, st))) return rc;
     }
     return JPEGB200_OK;
 }
@@ -441,9 +425,8 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
     cudaSetDevice(enc->device);
     cudaDeviceSynchronize();
     harvest_events(enc);
-    for (DeviceBuffer *b : {&enc->coef, &enc->blockinfo, &enc->blockoff, &enc->tilebase, &enc->lookback, &enc->image_bits,
-                            &enc->image_base, &enc->packed, &enc->image_ff, &enc->aclut, &enc->misc, &enc->host_in,
-                            &enc->host_scan})
+    for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->strips, &enc->lookback, &enc->image_bits, &enc->image_bytes,
+                            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan})
         b->release();
     delete enc;
 }
@@ -491,7 +474,7 @@ extern "C" int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb20
         return JPEGB200_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int rc = prepare(enc, batch->d_rgb, batch->width, batch->height, batch->count, batch->image_stride);
+    int rc = prepare(enc, batch->d_rgb, batch->width, batch->height, batch->count, batch->image_stride, 0);
     if (rc) return rc;
     return encode_launch(enc, d_scan, scan_capacity, d_scan_offsets, st);
 }
@@ -525,7 +508,7 @@ extern "C" int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out
     out->flagged_coefficients = flagged;
     out->kernel_launches = enc->launches;
     out->packed_bytes = 0;
-    if (enc->args.count > 0 && enc->image_bits.ptr) {
+    if (enc->args.count > 0 && enc->image_bits.ptr && !enc->stripe_ready) {
         std::vector<uint64_t> bits((size_t)enc->args.count);
         JB_CUDA(cudaMemcpy(bits.data(), enc->image_bits.ptr, bits.size() * 8, cudaMemcpyDeviceToHost));
         for (uint64_t b : bits) out->packed_bytes += (b + 7) / 8;
@@ -544,23 +527,33 @@ extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t
     return JPEGB200_OK;
 }
 
+// per-block bit cost, reconstructed from K1's strip-local offsets and strip records exactly the
+// way K2 consumes them (first block of a strip: DC difference against the previous strip's last DC)
 extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks)
 {
     if (!enc || !host_bits || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
     JB_CUDA(cudaSetDevice(enc->device));
     JB_CUDA(cudaDeviceSynchronize());
-    // bit cost of block b = offset(b+1) - offset(b) within its image
-    const EntropyArgs &a = enc->args;
-    std::vector<uint32_t> off((size_t)enc->total_blocks);
-    std::vector<uint64_t> tb((size_t)a.tiles * a.count), ib((size_t)a.count);
-    JB_CUDA(cudaMemcpy(off.data(), a.blockoff, off.size() * 4, cudaMemcpyDeviceToHost));
-    JB_CUDA(cudaMemcpy(tb.data(), a.tilebase, tb.size() * 8, cudaMemcpyDeviceToHost));
-    JB_CUDA(cudaMemcpy(ib.data(), a.image_bits, ib.size() * 8, cudaMemcpyDeviceToHost));
-    for (uint64_t b = 0; b < nblocks; ++b) {
-        const uint64_t img = b / a.nb, lb = b % a.nb;
-        const uint64_t cur = tb[img * a.tiles + lb / K2_TILE] + off[b];
-        const uint64_t nxt = lb + 1 < a.nb ? tb[img * a.tiles + (lb + 1) / K2_TILE] + off[b + 1] : ib[img];
-        host_bits[b] = (uint32_t)(nxt - cur);
+    const PackArgs &a = enc->args;
+    std::vector<uint32_t> info((size_t)enc->total_blocks);
+    std::vector<StripRec> recs((size_t)a.strips_avail * a.count);
+    JB_CUDA(cudaMemcpy(info.data(), a.blkinfo, info.size() * 4, cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpy(recs.data(), a.strips, recs.size() * sizeof(StripRec), cudaMemcpyDeviceToHost));
+    uint64_t done = 0;
+    for (int img = 0; img < a.count && done < nblocks; ++img) {
+        for (uint32_t s = 0; s < a.strips_avail && done < nblocks; ++s) {
+            const uint32_t brow = s / a.spr, sx = s % a.spr;
+            const uint32_t vb = std::min<uint32_t>(32u, a.bw - sx * 32u);
+            const uint64_t b0 = (uint64_t)img * a.nb_avail + (uint64_t)brow * a.bw + sx * 32u;
+            const StripRec &r = recs[(size_t)img * a.strips_avail + s];
+            const int pred = s == 0 ? (int)a.dc_pred0 : (int)recs[(size_t)img * a.strips_avail + s - 1].last_dc;
+            const uint32_t fix = enc->tables.dc_len[bit_length((int)r.first_dc - pred)];
+            for (uint32_t l = 0; l < vb; ++l) {
+                const uint32_t cur = info[b0 + l] & 0xFFFFu;
+                const uint32_t nxt = l + 1 < vb ? (info[b0 + l + 1] & 0xFFFFu) : r.bits;
+                if (b0 + l < nblocks) { host_bits[b0 + l] = nxt - cur + (l == 0 ? fix : 0u); ++done; }
+            }
+        }
     }
     return JPEGB200_OK;
 }
@@ -568,81 +561,51 @@ extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t 
 // ---- C ABI: MCU-row stripes -------------------------------------------------------------
 
 extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
-                                       jpegb200_stripe_summary *host_out, void *cuda_stream)
+                                       int halo_rows, jpegb200_stripe_summary *host_out, void *cuda_stream)
 {
     if (!host_out) return JPEGB200_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int rc = prepare(enc, d_rgb, width, stripe_height, 1, 0);
+    int rc = prepare(enc, d_rgb, width, stripe_height, 1, 0, halo_rows);
     if (rc) return rc;
     enc->launches = 0;
     if ((rc = launch_block_kernel(enc, st))) return rc;
-    // pass 1 of the scan with predictor 0 only to learn the stripe's total; offsets are
-    // recomputed in jpegb200_stripe_pack once the true predictor and bit phase are known.
-    enc->args.packed_capacity = 0;                          // no word clearing in this pass
-    if ((rc = launch_bit_scan(enc, st))) return rc;
-    uint32_t first = 0, last = 0;
-    uint64_t bits = 0;
-    JB_CUDA(cudaMemcpyAsync(&first, enc->blockinfo.ptr, 4, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaMemcpyAsync(&last, static_cast<uint32_t *>(enc->blockinfo.ptr) + (enc->total_blocks - 1), 4,
-                            cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaMemcpyAsync(&bits, enc->image_bits.ptr, 8, cudaMemcpyDeviceToHost, st));
+    const PackArgs &a = enc->args;
+    std::vector<StripRec> recs(a.strips_owned);
+    JB_CUDA(cudaMemcpyAsync(recs.data(), a.strips, recs.size() * sizeof(StripRec), cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
-    host_out->first_dc = (int16_t)(first & 0xFFFFu);
-    host_out->last_dc = (int16_t)(last & 0xFFFFu);
+    uint64_t bits = 0;
+    int pred = 0;
+    for (const StripRec &r : recs) {
+        bits += r.bits + enc->tables.dc_len[bit_length((int)r.first_dc - pred)];
+        pred = r.last_dc;
+    }
+    host_out->first_dc = recs.front().first_dc;
+    host_out->last_dc = recs.back().last_dc;
     host_out->reserved = 0;
     host_out->bits_pred0 = bits;
     enc->stripe_ready = true;
     return JPEGB200_OK;
 }
 
-extern "C" int jpegb200_stripe_pack(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin,
-                                    jpegb200_stripe_packed *host_out, void *cuda_stream)
+extern "C" int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin, uint8_t *d_scan,
+                                      uint64_t scan_capacity, uint64_t *host_scan_bytes, void *cuda_stream)
 {
-    if (!enc || !host_out || !enc->stripe_ready) {
-        g_last_error = "jpegb200_stripe_pack without a preceding jpegb200_stripe_analyze";
+    if (!enc || !d_scan || !host_scan_bytes || !enc->stripe_ready) {
+        g_last_error = "jpegb200_stripe_encode without a preceding jpegb200_stripe_analyze";
         return JPEGB200_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     JB_CUDA(cudaSetDevice(enc->device));
-    EntropyArgs &a = enc->args;
+    PackArgs &a = enc->args;
     a.dc_pred0 = dc_predictor;
     a.bit_phase = (uint32_t)(bit_begin & 7u);
-    a.packed_capacity = ((a.nb * (uint64_t)enc->bytes_per_block + 15) & ~15ull) + 32;
-    JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));   // second scan over the same tiles
-    int rc = 0;
-    if ((rc = launch_bit_scan(enc, st))) return rc;
-    if ((rc = launch_pack(enc, st))) return rc;
-    uint64_t bits = 0;
-    JB_CUDA(cudaMemcpyAsync(&bits, enc->image_bits.ptr, 8, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    if ((rc = jpegb200_encoder_status(enc, cuda_stream))) return rc;
-    const uint64_t nbytes = (bits + a.bit_phase + 7) >> 3;
-    uint8_t head = 0, tail = 0;
-    JB_CUDA(cudaMemcpyAsync(&head, enc->packed.ptr, 1, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaMemcpyAsync(&tail, static_cast<uint8_t *>(enc->packed.ptr) + (nbytes - 1), 1, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    host_out->bit_begin = bit_begin;
-    host_out->bit_end = bit_begin + bits;
-    host_out->head_byte = head;
-    host_out->tail_byte = tail;
-    return JPEGB200_OK;
-}
-
-extern "C" int jpegb200_stripe_finish(jpegb200_encoder *enc, uint32_t or_into_last_byte, int owns_first_byte,
-                                      int is_last_stripe, uint8_t *d_scan, uint64_t scan_capacity,
-                                      uint64_t *host_scan_bytes, void *cuda_stream)
-{
-    (void)is_last_stripe;           // the zero padding of the final byte is already in the packed words
-    if (!enc || !d_scan || !host_scan_bytes || !enc->stripe_ready) return JPEGB200_ERR_ARG;
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    JB_CUDA(cudaSetDevice(enc->device));
-    EntropyArgs &a = enc->args;
-    a.scan = d_scan;
-    a.scan_capacity = scan_capacity;
+    a.out = d_scan;
+    a.out_capacity = scan_capacity;
+    a.out_slot = 0;
     a.scan_offsets = misc_offsets(enc);
-    JB_CUDA(cudaMemsetAsync(misc_offsets(enc), 0, 16, st));
+    JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));   // idempotent re-runs
     int rc = 0;
-    if ((rc = launch_stuff(enc, StuffArgs{0, owns_first_byte ? 0u : 1u, or_into_last_byte & 0xFFu}, st))) return rc;
+    if ((rc = launch_entropy(enc, st))) return rc;
     uint64_t offs[2] = {0, 0};
     JB_CUDA(cudaMemcpyAsync(offs, misc_offsets(enc), 16, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
@@ -691,7 +654,7 @@ extern "C" int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_r
     uint8_t *d_scan = static_cast<uint8_t *>(enc->host_scan.ptr);
     uint64_t *d_off = misc_offsets(enc);
     JB_CUDA(cudaMemcpyAsync(d_rgb, host_rgb, nrgb, cudaMemcpyHostToDevice, st));
-    if ((rc = prepare(enc, d_rgb, width, height, 1, 0))) return rc;
+    if ((rc = prepare(enc, d_rgb, width, height, 1, 0, 0))) return rc;
     if ((rc = encode_launch(enc, d_scan, cap, d_off, st))) return rc;
     uint64_t offs[2] = {0, 0};
     uint32_t err = 0;

@@ -1,0 +1,488 @@
+// scan_pack.cuh -- K2, the fused entropy kernel: bit-offset scan + Huffman bit packing +
+// 0xFF byte stuffing in ONE launch (plus the two small batch-mode helpers).
+//
+// The reference's entropy stage is one serial chain: DC prediction across all blocks
+// (rle.c:59-70) and one contiguous MSB-first bit stream (huffman.c:35-62) with a zero byte
+// stuffed after every 0xFF (huffman.c:26-32) and a zero-padded last byte (huffman.c:65-81).
+//
+// K1 leaves, per 32-block strip, a record {bits, first DC, last DC} and per block its bit
+// offset inside the strip, so everything cross-block collapses to two prefix sums:
+//
+//   tile = 4 consecutive strips (<= 128 blocks), one CTA, warp w <-> strip, lane <-> block
+//   1. warp 0 adds the DC-difference cost of each strip's first block (needs the previous
+//      strip's last DC), sums the tile, publishes the aggregate and obtains the tile's bit
+//      offset by decoupled look-back over the image's earlier tiles;
+//   2. every lane re-derives its block's symbols from the 64 int8 coefficients (only up to
+//      the last non-zero one) and appends code+amplitude bits to a register accumulator that
+//      is flushed word-wise into a shared-memory window (atomicOr only on the two words a
+//      block shares with its neighbours);
+//   3. bytes are owned by the tile that holds their first bit: the last, partial byte is
+//      completed by encoding the next tile's first block(s) clipped at the byte boundary, the
+//      first partial byte is skipped -- no bits ever cross CTAs through global memory;
+//   4. 0xFF bytes of the tile's byte range are counted, a second look-back gives the number
+//      of stuffed zeros before the tile, and the stuffed bytes go straight to the output.
+#pragma once
+
+#include "common.cuh"
+
+namespace jb {
+
+constexpr int K2_WARPS = 4;                                    // strips per tile
+constexpr int K2_THREADS = K2_WARPS * 32;
+constexpr int K2_MAX_BLOCK_BITS = 1472;                        // >= 14 + 63*23 = 1463
+constexpr int K2_WIN_WORDS = (K2_THREADS * K2_MAX_BLOCK_BITS) / 32 + 8;
+
+// one record per strip, written by K1
+struct __align__(8) StripRec {
+    uint32_t bits;      // bit cost of the strip's blocks, WITHOUT the DC-difference code of its first block
+    int16_t first_dc;   // quantized DC of the strip's first block
+    int16_t last_dc;    // quantized DC of the strip's last block
+};
+
+// per-block word written by K1: [15:0] bit offset inside the strip (same convention as
+// StripRec.bits: the first block's DC-difference code not counted), [21:16] index of the last
+// non-zero AC coefficient (0 = none)
+__host__ __device__ __forceinline__ uint32_t blk_pack(uint32_t off, uint32_t last) { return off | (last << 16); }
+
+// device table block (one allocation per encoder): bit-cost LUT for K1, code tables for K2
+constexpr int ACLUT_ROWS = 63;                                 // zero run 0..62
+constexpr int ACLUT_STRIDE = 260;                              // 256 + 4: rows start in different banks
+constexpr int TBL_ACLUT = 0;                                   // uint8  [63][260] + EOB length at [16380]
+constexpr int TBL_DC_LEN = 16384;                              // uint8  [16]   DC code length + size  (K1 stages [0, 16400))
+constexpr int TBL_AC_CODE = 16400;                             // uint32 [256]  (code << 8) | len per (run<<4|size)
+constexpr int TBL_DC_CODE = TBL_AC_CODE + 1024;                // uint32 [16]   (code << 8) | len per size class
+constexpr int TBL_BYTES = TBL_DC_CODE + 64 + 48;               // 17536
+
+constexpr int K2_STAGE_STRIDE = 17;                            // words per lane in the coefficient staging area
+constexpr int K2_SMEM = (K2_WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE) * 4;
+
+struct PackArgs {
+    const uint8_t *tables;         // device table block (TBL_* offsets)
+    const int8_t *coef;            // [count*nb_avail][64] zig-zag int8
+    const uint32_t *blkinfo;       // [count*nb_avail]
+    const StripRec *strips;        // [count*strips_avail]
+    uint64_t *bit_state;           // [count*tiles] look-back state, bits
+    uint64_t *ff_state;            // [count*tiles] look-back state, stuffed zeros
+    uint8_t *out;                  // stuffed bytes: caller's buffer (count==1) or per-image slots (batch)
+    uint64_t out_capacity;         // bytes available per image at `out`
+    uint64_t out_slot;             // byte distance between images at `out` (batch), 0 for count==1
+    uint64_t *image_bytes;         // [count] stuffed size of each image
+    uint64_t *image_bits;          // [count] total bits of each image (owned blocks)
+    uint64_t *scan_offsets;        // count==1: scan_offsets[0..1] written here; batch: written by k_layout
+    uint32_t *err;
+    uint32_t strips_owned;         // strips per image that belong to the stream
+    uint32_t strips_avail;         // >= strips_owned: strips K1 produced (stripe halo)
+    uint32_t spr, bw;              // strips per block row, blocks per block row
+    uint32_t nb_avail;             // blocks per image K1 produced
+    int tiles;                     // tiles per image (over owned strips)
+    int count;
+    int16_t dc_pred0;              // DC predictor of the image's first block (0; stripes: previous stripe's last DC)
+    uint32_t bit_phase;            // bit offset of the first bit inside byte 0 (0; stripes: global phase & 7)
+};
+
+__device__ __forceinline__ int magnitude_class(int v)          // rle.c:9-22
+{
+    const int a = v < 0 ? -v : v;
+    return 32 - __clz(a);
+}
+
+__device__ __forceinline__ uint32_t strip_blocks(uint32_t strip_in_image, uint32_t spr, uint32_t bw)
+{
+    const uint32_t sx = strip_in_image % spr;
+    return min(32u, bw - sx * 32u);
+}
+
+// MSB-first bit appender with a 64-bit register accumulator.  The window word that holds the
+// block's first bit and the one that holds its last bit may be shared with the neighbouring
+// blocks (atomicOr); words in between belong to this block alone (plain store).
+struct BitWriter {
+    uint32_t *win;
+    uint64_t acc;
+    uint32_t wi, fill;
+    bool first;
+    __device__ __forceinline__ void start(uint32_t *w, uint32_t relbit)
+    {
+        win = w;
+        wi = relbit >> 5;
+        fill = relbit & 31u;
+        acc = 0;
+        first = true;
+    }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n)            // n in 1..26, v < 2^n
+    {
+        acc |= (uint64_t)v << (64u - fill - n);
+        fill += n;
+        if (fill >= 32u) {
+            const uint32_t word = (uint32_t)(acc >> 32);
+            if (first) { atomicOr(win + wi, word); first = false; }
+            else win[wi] = word;
+            acc <<= 32;
+            fill -= 32u;
+            ++wi;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (fill) atomicOr(win + wi, (uint32_t)(acc >> 32));
+    }
+};
+
+// append with clipping at bit `limit` (window-relative); used only for the halo blocks
+__device__ __forceinline__ void put_clipped(uint32_t *win, uint32_t &pos, uint32_t limit, uint32_t v, uint32_t n)
+{
+    if (pos >= limit) return;
+    if (pos + n > limit) {
+        const uint32_t keep = limit - pos;
+        v >>= (n - keep);
+        n = keep;
+    }
+    const uint64_t x = ((uint64_t)v << (64u - n)) >> (pos & 31u);
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    if (hi) atomicOr(win + (pos >> 5), hi);
+    if (lo) atomicOr(win + (pos >> 5) + 1, lo);
+    pos += n;
+}
+
+// 4-bit mask of the non-zero bytes of a word (bit j <-> byte j)
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
+{
+    const uint32_t t = (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;   // 0x80 per non-zero byte
+    return (t * 0x00204081u) >> 28;                                             // gather bits 7,15,23,31
+}
+
+// Walk one block's symbols (rle.c:59-124) and hand (value, nbits) pairs (huffman.c:145-173) to
+// emit(), which returns false to stop early.  sw: the block's 16 coefficient words in shared
+// memory (zig-zag order, int8).
+// The lane first builds the 63-bit map of its non-zero AC coefficients and then visits only
+// those: the loop trip count is the lane's symbol count, so a warp runs max-over-lanes symbols
+// instead of one divergent branch per coefficient position.
+template <typename Emit>
+__device__ __forceinline__ void encode_block(const uint32_t *sw, int prev_dc, int last, const uint32_t *s_ac,
+                                             const uint32_t *s_dc, Emit emit)
+{
+    const uint32_t w0 = sw[0];
+    {
+        const int diff = (int)(int8_t)(w0 & 0xFFu) - prev_dc;                          // rle.c:68-70
+        const int sz = magnitude_class(diff);
+        const uint32_t hc = s_dc[sz];
+        const uint32_t amp = (uint32_t)(diff > 0 ? diff : diff - 1) & ((1u << sz) - 1u);   // rle.c:24-35, huffman.c:39
+        if (!emit(((hc >> 8) << sz) | amp, (hc & 0xFFu) + sz)) return;
+    }
+    uint32_t mlo = nonzero_nibble(w0 & 0xFFFFFF00u), mhi = 0;     // bit k <-> zig-zag position k
+    const int lastw = last >> 2;
+#pragma unroll
+    for (int w = 1; w < 8; ++w)
+        if (w <= lastw) mlo |= nonzero_nibble(sw[w]) << (4 * w);
+#pragma unroll
+    for (int w = 8; w < 16; ++w)
+        if (w <= lastw) mhi |= nonzero_nibble(sw[w]) << (4 * (w - 8));
+    const int8_t *sb = reinterpret_cast<const int8_t *>(sw);
+    int prev = 0;                                                 // position of the previous non-zero (0 = DC)
+#pragma unroll 1
+    while (mlo | mhi) {
+        int k;
+        if (mlo) { k = __ffs((int)mlo) - 1; mlo &= mlo - 1; }
+        else { k = 32 + __ffs((int)mhi) - 1; mhi &= mhi - 1; }
+        const int v = sb[k];
+        int run = k - prev - 1;
+        prev = k;
+        while (run >= 16) {                                                            // ZRL, rle.c:99-103
+            const uint32_t z = s_ac[0xF0];
+            if (!emit(z >> 8, z & 0xFFu)) return;
+            run -= 16;
+        }
+        const int sz = magnitude_class(v);
+        const uint32_t hc = s_ac[(run << 4) | sz];
+        const uint32_t amp = (uint32_t)(v > 0 ? v : v - 1) & ((1u << sz) - 1u);
+        if (!emit(((hc >> 8) << sz) | amp, (hc & 0xFFu) + sz)) return;
+    }
+    if (last < 63) {                                                                   // EOB, rle.c:121-123
+        const uint32_t e = s_ac[0x00];
+        emit(e >> 8, e & 0xFFu);
+    }
+}
+
+__device__ __forceinline__ uint32_t count_ff_bytes(uint32_t w)
+{
+    uint32_t x = w & (w >> 4);
+    x &= x >> 2;
+    x &= x >> 1;
+    return __popc(x & 0x01010101u);
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+k_scan_pack_stuff(const PackArgs a)
+{
+    extern __shared__ __align__(16) uint32_t win[];          // [K2_WIN_WORDS] bit window, then the staging area
+    uint32_t *stage = win + K2_WIN_WORDS + (threadIdx.x * K2_STAGE_STRIDE);   // this lane's 16 coefficient words
+    __shared__ uint32_t s_ac[256], s_dc[16];
+    __shared__ uint64_t s_strip_base[K2_WARPS];     // window-independent bit offset of each strip (incl. phase)
+    __shared__ uint32_t s_strip_fix[K2_WARPS];      // DC-difference cost of the strip's first block
+    __shared__ uint64_t s_begin, s_end, s_ffexcl;
+    __shared__ uint32_t s_warp[K2_WARPS], s_carry, s_tile_bits;
+    __shared__ uint64_t s_scratch[12];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, img = blockIdx.y;
+    const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
+    const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
+    const uint32_t nstrips = min((uint32_t)K2_WARPS, a.strips_owned - strip0);
+    const bool last_tile = tile == a.tiles - 1;
+
+    for (int i = tid; i < 256; i += K2_THREADS) s_ac[i] = reinterpret_cast<const uint32_t *>(a.tables + TBL_AC_CODE)[i];
+    if (tid < 16) s_dc[tid] = reinterpret_cast<const uint32_t *>(a.tables + TBL_DC_CODE)[tid];
+
+    // ---- 0. fetch this lane's block before any waiting (loads do not depend on the offsets) ------
+    const uint64_t img_block0 = (uint64_t)img * a.nb_avail;
+    const uint32_t my_strip = strip0 + warp;
+    const bool have = (uint32_t)warp < nstrips && (uint32_t)lane < strip_blocks(my_strip, a.spr, a.bw);
+    uint32_t info = 0;
+    int my_dc = 0;
+    if (have) {
+        const uint32_t brow = my_strip / a.spr, sx = my_strip - brow * a.spr;
+        const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lane;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + b * 64);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 q = src[i];
+            stage[4 * i] = q.x; stage[4 * i + 1] = q.y; stage[4 * i + 2] = q.z; stage[4 * i + 3] = q.w;
+            if (i == 0) my_dc = (int)(int8_t)(q.x & 0xFFu);
+        }
+        info = a.blkinfo[b];
+    }
+    // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
+    // previous strip's last block for lane 0
+    int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+    if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
+
+    // ---- 1. tile bit offset --------------------------------------------------------------
+    if (warp == 0) {
+        uint32_t tot = 0, fix = 0;
+        if ((uint32_t)lane < nstrips) {
+            const StripRec r = recs[strip0 + lane];
+            const int pred = strip0 + lane == 0 ? (int)a.dc_pred0 : (int)recs[strip0 + lane - 1].last_dc;
+            fix = c_dc_len[magnitude_class((int)r.first_dc - pred)];
+            tot = r.bits + fix;
+        }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < K2_WARPS; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const uint32_t tile_bits = __shfl_sync(0xffffffffu, incl, K2_WARPS - 1);
+        if (lane == 0) {
+            st_volatile_u64(a.bit_state + (uint64_t)img * a.tiles + tile,
+                            lb_pack(1u, tile == 0 ? LB_PREFIX : LB_AGGREGATE, tile_bits));
+            s_tile_bits = tile_bits;
+        }
+        if (lane < K2_WARPS) {
+            s_strip_base[lane] = incl - tot;                      // tile-relative for now
+            s_strip_fix[lane] = fix;
+        }
+    }
+    __syncthreads();
+    {
+        uint64_t *state = a.bit_state + (uint64_t)img * a.tiles;
+        const uint64_t excl = lookback_exclusive_cta(state, tile, a.err, s_scratch);
+        if (tid == 0) {
+            if (tile != 0) st_volatile_u64(state + tile, lb_pack(1u, LB_PREFIX, excl + s_tile_bits));
+            s_begin = excl + a.bit_phase;
+            s_end = excl + a.bit_phase + s_tile_bits;
+            if (last_tile) a.image_bits[img] = excl + s_tile_bits;
+        }
+        if (tid < K2_WARPS) s_strip_base[tid] += excl + a.bit_phase;
+    }
+    __syncthreads();
+    const uint64_t begin = s_begin, end = s_end;
+    const uint64_t w0 = begin >> 5;
+    const uint32_t nwords = (uint32_t)(((end + 31) >> 5) - w0);
+    for (uint32_t i = tid; i < nwords + 2; i += K2_THREADS) win[i] = 0;
+    __syncthreads();
+
+    // ---- 2. pack this tile's blocks --------------------------------------------------------
+    if (have) {
+        const uint64_t off = s_strip_base[warp] + (lane ? s_strip_fix[warp] : 0u) + (info & 0xFFFFu);
+        BitWriter bw;
+        bw.start(win, (uint32_t)(off - (w0 << 5)));
+        encode_block(stage, prev_dc, (int)((info >> 16) & 63u), s_ac, s_dc,
+                     [&](uint32_t v, uint32_t n) { bw.put(v, n); return true; });
+        bw.finish();
+    }
+
+    // ---- 3. complete the last owned byte with the next tile's leading bits (at most 7) -----------
+    // Bytes are owned by the tile that holds their first bit.  Runs concurrently with the packing
+    // above: it only ORs into bits at or after `end`.
+    const uint64_t limit = (end + 7) & ~7ull;                    // first bit NOT owned by this tile
+    if (tid == 0 && (end & 7u) && !(last_tile && a.strips_avail == a.strips_owned)) {
+        uint32_t pos = (uint32_t)(end - (w0 << 5));
+        const uint32_t lim = (uint32_t)(limit - (w0 << 5));
+        uint32_t st = strip0 + nstrips;                          // raster successor of the tile's last block
+        int hprev = (int)recs[st - 1].last_dc;
+        uint32_t lb = 0;
+        for (int n = 0; n < 2 && pos < lim && st < a.strips_avail; ++n) {
+            const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
+            const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) stage[i] = src[i];
+            const uint32_t hinfo = a.blkinfo[b];
+            encode_block(stage, hprev, (int)((hinfo >> 16) & 63u), s_ac, s_dc, [&](uint32_t v, uint32_t nb) {
+                put_clipped(win, pos, lim, v, nb);
+                return pos < lim;
+            });
+            hprev = (int)(int8_t)(stage[0] & 0xFFu);
+            if (++lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. stuffing ------------------------------------------------------------------------------
+    // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
+    const uint64_t B0 = (begin + 7) >> 3, B1 = (end + 7) >> 3;
+    const uint32_t wb0 = (uint32_t)(B0 - 4 * w0), wb1 = (uint32_t)(B1 - 4 * w0);     // window byte range
+    const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;                        // window word range [wfirst, wlast)
+    auto masked_word = [&](uint32_t i) -> uint32_t {
+        uint32_t v = win[i];
+        const uint32_t lo = i * 4, hi = lo + 4;                   // bytes lo..hi-1 (MSB first)
+        if (lo < wb0) v &= 0xFFFFFFFFu >> (8 * (wb0 - lo));
+        if (hi > wb1) v &= wb1 > lo ? 0xFFFFFFFFu << (8 * (hi - wb1)) : 0u;
+        return v;
+    };
+    uint32_t mine = 0;
+    for (uint32_t i = wfirst + tid; i < wlast; i += K2_THREADS) mine += count_ff_bytes(masked_word(i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_warp[warp] = mine;
+    __syncthreads();
+    {
+        uint32_t tile_ff = 0;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; ++w) tile_ff += s_warp[w];
+        uint64_t *state = a.ff_state + (uint64_t)img * a.tiles;
+        if (tid == 0) st_volatile_u64(state + tile, lb_pack(1u, tile == 0 ? LB_PREFIX : LB_AGGREGATE, tile_ff));
+        const uint64_t excl = lookback_exclusive_cta(state, tile, a.err, s_scratch);
+        if (tid == 0) {
+            if (tile != 0) st_volatile_u64(state + tile, lb_pack(1u, LB_PREFIX, excl + tile_ff));
+            s_ffexcl = excl;
+            s_carry = 0;
+            if (last_tile) {
+                const uint64_t origin0 = ((uint64_t)a.bit_phase + 7) >> 3;
+                const uint64_t size = B1 - origin0 + excl + tile_ff;
+                a.image_bytes[img] = size;
+                if (a.count == 1) {
+                    a.scan_offsets[0] = 0;
+                    a.scan_offsets[1] = size;
+                }
+                if (size > a.out_capacity) atomicOr(a.err, a.count == 1 ? ERRBIT_OUTPUT : ERRBIT_WORKSPACE);
+            }
+        }
+    }
+    __syncthreads();
+    const uint64_t origin = ((uint64_t)a.bit_phase + 7) >> 3;     // first stream byte this image/stripe owns
+    uint8_t *out = a.out + (uint64_t)img * a.out_slot;
+    const uint64_t out_base = (B0 - origin) + s_ffexcl;           // output index of window byte wb0
+    for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
+        const uint32_t i = i0 + tid;
+        const uint32_t v = i < wlast ? masked_word(i) : 0u;
+        const uint32_t cnt = count_ff_bytes(v);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = s_carry + incl - cnt;
+        uint32_t round_total = 0;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; ++w) {
+            const uint32_t ws = s_warp[w];
+            if (w < warp) before += ws;
+            round_total += ws;
+        }
+        if (i < wlast) {
+            const uint32_t raw = win[i];
+            uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t wb = i * 4 + k;
+                if (wb >= wb0 && wb < wb1) {
+                    const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
+                    if (pos < a.out_capacity) out[pos] = byte;
+                    ++pos;
+                    if (byte == 0xFF) {                             // huffman.c:29-31
+                        if (pos < a.out_capacity) out[pos] = 0x00;
+                        ++pos;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += round_total;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// batch mode: exclusive scan of the stuffed image sizes -> scan_offsets[count+1]  (one CTA)
+__global__ void __launch_bounds__(1024)
+k_layout(const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ scan_offsets, const int count,
+         const uint64_t scan_capacity, uint32_t *err)
+{
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < count; base += 1024) {
+        const int i = base + tid;
+        const uint64_t v = i < count ? image_bytes[i] : 0;
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        uint64_t wex = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const uint64_t ws = warp_sums[w];
+            if (w < warp) wex += ws;
+            tot += ws;
+        }
+        const uint64_t excl = carry_s + wex + incl - v;
+        if (i < count) {
+            scan_offsets[i] = excl;
+            if (i == count - 1) {
+                scan_offsets[count] = excl + v;
+                if (excl + v > scan_capacity) atomicOr(err, ERRBIT_OUTPUT);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry_s += tot;
+        __syncthreads();
+    }
+}
+
+// batch mode: move every image's stuffed bytes from its slot to its final offset
+__global__ void __launch_bounds__(256)
+k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const uint64_t *__restrict__ image_bytes,
+          const uint64_t *__restrict__ scan_offsets, uint8_t *__restrict__ scan, const uint64_t scan_capacity)
+{
+    const int img = blockIdx.y;
+    const uint64_t n = image_bytes[img], dst0 = scan_offsets[img];
+    if (dst0 + n > scan_capacity) return;                        // flagged by k_layout
+    const uint8_t *src = slots + (uint64_t)img * slot_stride;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += (uint64_t)gridDim.x * blockDim.x * 16) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(src + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (i + k < n) scan[dst0 + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
+}  // namespace jb

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Batch, Stats, StripePacked, StripeSummary, check, load_library
+from ._lib import Batch, Stats, StripeSummary, check, load_library
 
 
 def _torch():
@@ -114,7 +114,7 @@ class DeviceEncoder:
         calls = (C.c_uint64 * 8)()
         check(self.lib.jpegb200_encoder_kernel_times(self.handle, ms, calls, int(reset)), "kernel_times")
         return {"ms": list(ms), "calls": [int(c) for c in calls],
-                "names": ["fused_block", "bit_scan", "pack", "stuff", "image_layout", "zero_words", "", ""]}
+                "names": ["fused_block", "scan_pack_stuff", "batch_layout", "batch_compact", "", "", "", ""]}
 
     def coefficients(self, nblocks: int) -> np.ndarray:
         out = np.empty((nblocks, 64), np.int16)
@@ -127,21 +127,18 @@ class DeviceEncoder:
         return out
 
     # ---- stripes -------------------------------------------------------------------
-    def stripe_analyze(self, d_rgb, w: int, stripe_h: int) -> dict:
+    def stripe_analyze(self, d_rgb, w: int, stripe_h: int, halo_rows: int = 0) -> dict:
+        """K1 over the stripe's rows (+ halo rows of the next stripe) -> boundary summary."""
         s = StripeSummary()
-        check(self.lib.jpegb200_stripe_analyze(self.handle, d_rgb.data_ptr(), w, stripe_h, C.byref(s), self._stream()),
-              "stripe_analyze")
+        check(self.lib.jpegb200_stripe_analyze(self.handle, d_rgb.data_ptr(), w, stripe_h, halo_rows, C.byref(s),
+                                               self._stream()), "stripe_analyze")
         return {"first_dc": s.first_dc, "last_dc": s.last_dc, "bits_pred0": s.bits_pred0}
 
-    def stripe_pack(self, dc_pred: int, bit_begin: int) -> dict:
-        p = StripePacked()
-        check(self.lib.jpegb200_stripe_pack(self.handle, dc_pred, bit_begin, C.byref(p), self._stream()), "stripe_pack")
-        return {"bit_begin": p.bit_begin, "bit_end": p.bit_end, "head_byte": p.head_byte, "tail_byte": p.tail_byte}
-
-    def stripe_finish(self, or_last: int, owns_first: bool, is_last: bool, scan) -> int:
+    def stripe_encode(self, dc_pred: int, bit_begin: int, scan) -> int:
+        """K2 at the stripe's true predictor and global bit offset -> number of stuffed bytes."""
         n = C.c_uint64(0)
-        check(self.lib.jpegb200_stripe_finish(self.handle, or_last, int(owns_first), int(is_last), scan.data_ptr(),
-                                              scan.numel(), C.byref(n), self._stream()), "stripe_finish")
+        check(self.lib.jpegb200_stripe_encode(self.handle, dc_pred, bit_begin, scan.data_ptr(), scan.numel(),
+                                              C.byref(n), self._stream()), "stripe_encode")
         return int(n.value)
 
     # ---- synthetic inputs on the device --------------------------------------------
