@@ -112,49 +112,59 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *state, in
     return excl;
 }
 
-// CTA-wide variant: all 256 threads of the CTA take part, 256 predecessors per round (a few
-// hundred tiles resolve in one or two rounds instead of a dozen).  Every thread returns the
-// exclusive prefix.  s_scratch: 24 words of shared memory.  Must be called by the whole CTA.
-__device__ __forceinline__ uint64_t lookback_exclusive_cta(const uint64_t *state, int tile, uint32_t *err,
-                                                           uint64_t *s_scratch)
+// Grouped look-back (whole CTA).  Tiles of one segment publish their aggregate in agg[tile]
+// (bit 63 = valid) as soon as they know it; the last tile of every group of LB_GROUP tiles also
+// publishes its inclusive prefix in incl[group].  A tile's exclusive prefix is then
+//     incl[group - 1]  +  sum of agg[j] for the earlier tiles j of its own group,
+// and the (up to 1023) aggregate loads are independent: every thread issues all of its loads
+// back to back, so the whole look-back costs about one L2 round trip instead of a polling chain
+// (no thread ever re-reads a word that was already valid).  Only group boundaries form a serial
+// chain, one hop per 1024 tiles.  Spins are bounded; on timeout ERRBIT_LOOKBACK is set.
+constexpr int LB_GROUP = 1024;
+constexpr uint64_t LB_VALID = 1ull << 63;
+
+__device__ __forceinline__ uint64_t lb_wait(const uint64_t *p, uint32_t *err)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    uint32_t *s_first = reinterpret_cast<uint32_t *>(s_scratch);      // [8]  lane of the nearest PREFIX per warp (32: none)
-    uint64_t *s_sum = s_scratch + 4;                                  // [8]  per-warp sums
-    uint64_t excl = 0;
-    int base = tile - 1;
-    while (base >= 0) {
-        const int j = base - tid;
-        uint64_t v = 0;
-        uint32_t status = LB_PREFIX;                                  // virtual tile before tile 0: prefix 0
-        if (j >= 0) {
-            int spins = 0;
-            for (;;) {
-                v = ld_volatile_u64(state + j);
-                status = (uint32_t)(v >> LB_STATUS_SHIFT) & 3u;
-                if (status != 0) break;
-                if (++spins > (1 << 22)) { atomicOr(err, ERRBIT_LOOKBACK); status = LB_PREFIX; v = 0; break; }
-                __nanosleep(20);
-            }
-            v &= LB_VALUE_MASK;
-        }
-        const uint32_t pmask = __ballot_sync(0xffffffffu, status == LB_PREFIX);
-        if (lane == 0) s_first[warp] = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
-        __syncthreads();
-        int wstar = nwarp;                                            // nearest warp holding a PREFIX
-        for (int w = nwarp - 1; w >= 0; --w)
-            if (s_first[w] < 32u) wstar = w;
-        const bool take = warp < wstar || (warp == wstar && (uint32_t)lane <= s_first[wstar]);
-        uint64_t c = take ? v : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) s_sum[warp] = c;
-        __syncthreads();
-        for (int w = 0; w < nwarp; ++w) excl += s_sum[w];
-        __syncthreads();
-        if (wstar < nwarp) break;
-        base -= (int)blockDim.x;
+    uint64_t v = ld_volatile_u64(p);
+    int spins = 0;
+    while (!(v & LB_VALID)) {
+        if (++spins > (1 << 22)) { atomicOr(err, ERRBIT_LOOKBACK); return 0; }
+        __nanosleep(100);
+        v = ld_volatile_u64(p);
     }
+    return v & ~LB_VALID;
+}
+
+// s_scratch: 9 words of shared memory.  Must be called by the whole CTA (blockDim.x <= 256).
+__device__ __forceinline__ uint64_t lookback_grouped(const uint64_t *agg, const uint64_t *incl, int tile, uint32_t *err,
+                                                     uint64_t *s_scratch)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarp = nthreads >> 5;
+    const int g0 = (tile / LB_GROUP) * LB_GROUP;
+    uint64_t sum = 0;
+    if (tid == 0 && g0 > 0) sum = lb_wait(incl + (tile / LB_GROUP) - 1, err);
+    constexpr int BATCH = 8;
+    for (int j0 = g0 + tid; j0 < tile; j0 += nthreads * BATCH) {
+        uint64_t v[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int j = j0 + i * nthreads;
+            v[i] = j < tile ? ld_volatile_u64(agg + j) : LB_VALID;
+        }
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int j = j0 + i * nthreads;
+            if (!(v[i] & LB_VALID)) v[i] = lb_wait(agg + j, err);
+            sum += v[i] & ~LB_VALID;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();                       // s_scratch may still be read from a previous call
+    if (lane == 0) s_scratch[warp] = sum;
+    __syncthreads();
+    uint64_t excl = 0;
+    for (int w = 0; w < nwarp; ++w) excl += s_scratch[w];
     return excl;
 }
 

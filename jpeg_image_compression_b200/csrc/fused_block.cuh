@@ -55,6 +55,9 @@ struct StripCtx {
     int npx;                 // real pixels per row in the strip (<= 256)
     int vb;                  // 8x8 blocks in the strip (<= 32)
     uint32_t mispack;        // 16-byte phase of each of the 8 row pointers, 4 bits per row
+    // the block that precedes the strip in raster order (its DC is the strip's first predictor)
+    const uint8_t *halo;     // its top-left pixel; nullptr for the first strip of an image
+    int halo_rmax, halo_cmax;// last real row / column inside that block (edges replicate)
 };
 
 __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
@@ -75,6 +78,19 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
     c.mispack = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) c.mispack |= ((m0 + (uint32_t)min(r, c.rmax) * step) & 15u) << (4 * r);
+    if (sx > 0) {                                   // previous block is in the same block row
+        c.halo = c.row0 - 24;
+        c.halo_rmax = c.rmax;
+        c.halo_cmax = 7;
+    } else if (brow > 0) {                          // last block of the previous block row
+        const int hx0 = (g.bw - 1) * 8;
+        c.halo = c.row0 - (uint64_t)8u * c.pitch + (uint64_t)hx0 * 3u;
+        c.halo_rmax = 7;
+        c.halo_cmax = g.w - 1 - hx0;
+    } else {
+        c.halo = nullptr;
+        c.halo_rmax = c.halo_cmax = 0;
+    }
     return c;
 }
 
@@ -189,6 +205,14 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
 
     for (; s < total; s += nwarps) {
+        // luma sum of the raster-predecessor block: lane l covers row l/4, columns 2*(l%4) and +1;
+        // the loads are issued now and consumed after the transform
+        uint32_t halo_y = 0;
+        if (cur.halo) {
+            const uint8_t *hp = cur.halo + (uint64_t)((uint32_t)min(lane >> 2, cur.halo_rmax) * cur.pitch);
+            const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
+            halo_y = ((77u * p0[0] + 150u * p0[1] + 29u * p0[2]) >> 8) + ((77u * p1[0] + 150u * p1[1] + 29u * p1[2]) >> 8);
+        }
         cp_async_wait_all();
         __syncwarp();
 
@@ -350,11 +374,19 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             dst[2] = make_uint4(zw[8], zw[9], zw[10], zw[11]);
             dst[3] = make_uint4(zw[12], zw[13], zw[14], zw[15]);
         }
-        // DC-difference cost inside the strip (rle.c:68-76); the strip's first block is charged by K2,
-        // which knows the previous strip's last DC.  Then the strip-local exclusive bit offsets.
+        // DC-difference costs (rle.c:68-76).  The strip's first block is predicted from the block
+        // before the strip, whose quantized DC follows from its 64 luma values alone (an exact integer
+        // sum, same closed form as above).  The very first strip of an image is charged by K2 (its
+        // predictor is 0, or the previous stripe's last DC in multi-GPU runs).
         {
-            const int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
-            if (lane > 0 && lane < me.vb) my_bits += s_dclen[magnitude_class(my_dc - prev_dc)];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) halo_y += __shfl_xor_sync(0xffffffffu, halo_y, o);
+            int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+            if (lane == 0) {
+                const float f = __fmul_rn(c_ref_scale[0], (float)((int)halo_y - 8192));
+                prev_dc = (int)roundf(f * 0.0625f);
+            }
+            if (lane < me.vb && (lane > 0 || me.halo)) my_bits += s_dclen[magnitude_class(my_dc - prev_dc)];
             uint32_t incl = my_bits;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {

@@ -155,6 +155,7 @@ struct jpegb200_encoder {
     uint64_t lookback_words = 0;
     uint64_t total_blocks = 0;      // blocks K1 produced (all images, incl. stripe halo)
     uint64_t launches = 0;
+    int k2_ctas_per_sm[2] = {0, 0};
     bool stripe_ready = false;
     // optional per-kernel timing (cudaEvents on the launching stream)
     bool profiling = false;
@@ -185,7 +186,10 @@ static int upload_tables(jpegb200_encoder *enc)
             JB_CUDA(cudaMemcpyToSymbol(c_dc_code, t.dc_code, sizeof(t.dc_code)));
             JB_CUDA(cudaMemcpyToSymbol(c_ac_code, t.ac_code, sizeof(t.ac_code)));
             JB_CUDA(cudaFuncSetAttribute(k_fused_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_scan_pack_stuff, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_scan_pack_stuff<K2_SMALL_BLOCK_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         k2_smem(K2_SMALL_BLOCK_BITS)));
+            JB_CUDA(cudaFuncSetAttribute(k_scan_pack_stuff<K2_MAX_BLOCK_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         k2_smem(K2_MAX_BLOCK_BITS)));
             g_tables_uploaded[enc->device & 63] = true;
         }
     }
@@ -245,9 +249,10 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     if ((rc = enc->coef.reserve(tb * 64))) return rc;
     if ((rc = enc->blkinfo.reserve(tb * 4))) return rc;
     if ((rc = enc->strips.reserve(g.total_strips * sizeof(StripRec)))) return rc;
-    // look-back state of K2: one word per tile for the bit offsets, one for the stuffed-zero counts;
-    // contiguous, cleared by K1's prologue
-    enc->lookback_words = 2ull * (uint64_t)tiles * (uint64_t)count;
+    // grouped look-back state of K2 (aggregate per tile + inclusive prefix per 1024-tile group), once
+    // for the bit offsets and once for the stuffed-zero counts; contiguous, cleared by K1's prologue
+    const int groups = (tiles + LB_GROUP - 1) / LB_GROUP;
+    enc->lookback_words = ((uint64_t)tiles + 2ull * (uint64_t)groups) * (uint64_t)count;
     if ((rc = enc->lookback.reserve(enc->lookback_words * 8))) return rc;
     if ((rc = enc->image_bits.reserve((uint64_t)count * 8))) return rc;
     if ((rc = enc->image_bytes.reserve((uint64_t)count * 8))) return rc;
@@ -260,8 +265,9 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.coef = static_cast<const int8_t *>(enc->coef.ptr);
     a.blkinfo = static_cast<const uint32_t *>(enc->blkinfo.ptr);
     a.strips = static_cast<const StripRec *>(enc->strips.ptr);
-    a.bit_state = static_cast<uint64_t *>(enc->lookback.ptr);
-    a.ff_state = a.bit_state + (uint64_t)tiles * (uint64_t)count;
+    a.bit_incl = static_cast<uint64_t *>(enc->lookback.ptr);
+    a.ff_agg = a.bit_incl + (uint64_t)groups * (uint64_t)count;
+    a.ff_incl = a.ff_agg + (uint64_t)tiles * (uint64_t)count;
     a.out = count > 1 ? static_cast<uint8_t *>(enc->slots.ptr) : nullptr;
     a.out_capacity = count > 1 ? slot : 0;
     a.out_slot = count > 1 ? slot : 0;
@@ -322,13 +328,27 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     return JPEGB200_OK;
 }
 
-// K2: fused scan + pack + stuff, one CTA per tile of 8 strips
+// K2: fused scan + pack + stuff; persistent CTAs (never more than can be co-resident: tiles wait
+// on their predecessors) taking tiles of 4 strips in increasing order
 static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {
     const PackArgs &a = enc->args;
+    // window size: 64 bytes per block on average unless the caller asked for more workspace
+    const bool small = enc->bytes_per_block * 8 <= K2_SMALL_BLOCK_BITS;
+    const int smem = small ? k2_smem(K2_SMALL_BLOCK_BITS) : k2_smem(K2_MAX_BLOCK_BITS);
+    int &per_sm = enc->k2_ctas_per_sm[small ? 0 : 1];
+    if (per_sm == 0) {
+        int n = 0;
+        if (small) JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan_pack_stuff<K2_SMALL_BLOCK_BITS>, K2_THREADS, smem));
+        else JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan_pack_stuff<K2_MAX_BLOCK_BITS>, K2_THREADS, smem));
+        per_sm = n > 0 ? n : 1;
+    }
+    const uint64_t total = (uint64_t)a.tiles * (uint64_t)a.count;
+    const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);
     {
         TimedLaunch t(enc, st, KID_ENTROPY);
-        k_scan_pack_stuff<<<dim3((unsigned)a.tiles, (unsigned)a.count), K2_THREADS, K2_SMEM, st>>>(a);
+        if (small) k_scan_pack_stuff<K2_SMALL_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
+        else k_scan_pack_stuff<K2_MAX_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -528,7 +548,7 @@ extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t
 }
 
 // per-block bit cost, reconstructed from K1's strip-local offsets and strip records exactly the
-// way K2 consumes them (first block of a strip: DC difference against the previous strip's last DC)
+// way K2 consumes them
 extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks)
 {
     if (!enc || !host_bits || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
@@ -546,8 +566,8 @@ extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t 
             const uint32_t vb = std::min<uint32_t>(32u, a.bw - sx * 32u);
             const uint64_t b0 = (uint64_t)img * a.nb_avail + (uint64_t)brow * a.bw + sx * 32u;
             const StripRec &r = recs[(size_t)img * a.strips_avail + s];
-            const int pred = s == 0 ? (int)a.dc_pred0 : (int)recs[(size_t)img * a.strips_avail + s - 1].last_dc;
-            const uint32_t fix = enc->tables.dc_len[bit_length((int)r.first_dc - pred)];
+            // only the image's first DC symbol is not in K1's counts (its predictor is a run-time argument)
+            const uint32_t fix = s == 0 ? enc->tables.dc_len[bit_length((int)r.first_dc - (int)a.dc_pred0)] : 0u;
             for (uint32_t l = 0; l < vb; ++l) {
                 const uint32_t cur = info[b0 + l] & 0xFFFFu;
                 const uint32_t nxt = l + 1 < vb ? (info[b0 + l + 1] & 0xFFFFu) : r.bits;
@@ -573,12 +593,8 @@ extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_r
     std::vector<StripRec> recs(a.strips_owned);
     JB_CUDA(cudaMemcpyAsync(recs.data(), a.strips, recs.size() * sizeof(StripRec), cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
-    uint64_t bits = 0;
-    int pred = 0;
-    for (const StripRec &r : recs) {
-        bits += r.bits + enc->tables.dc_len[bit_length((int)r.first_dc - pred)];
-        pred = r.last_dc;
-    }
+    uint64_t bits = enc->tables.dc_len[bit_length((int)recs.front().first_dc)];   // first DC symbol, predictor 0
+    for (const StripRec &r : recs) bits += r.bits;
     host_out->first_dc = recs.front().first_dc;
     host_out->last_dc = recs.back().last_dc;
     host_out->reserved = 0;

@@ -11,7 +11,7 @@
 //   tile = 4 consecutive strips (<= 128 blocks), one CTA, warp w <-> strip, lane <-> block
 //   1. warp 0 adds the DC-difference cost of each strip's first block (needs the previous
 //      strip's last DC), sums the tile, publishes the aggregate and obtains the tile's bit
-//      offset by decoupled look-back over the image's earlier tiles;
+//      offset by a grouped look-back over the image's earlier tiles (common.cuh);
 //   2. every lane re-derives its block's symbols from the 64 int8 coefficients (only up to
 //      the last non-zero one) and appends code+amplitude bits to a register accumulator that
 //      is flushed word-wise into a shared-memory window (atomicOr only on the two words a
@@ -21,6 +21,7 @@
 //      first partial byte is skipped -- no bits ever cross CTAs through global memory;
 //   4. 0xFF bytes of the tile's byte range are counted, a second look-back gives the number
 //      of stuffed zeros before the tile, and the stuffed bytes go straight to the output.
+// CTAs are persistent and take tiles in increasing order.
 #pragma once
 
 #include "common.cuh"
@@ -29,19 +30,19 @@ namespace jb {
 
 constexpr int K2_WARPS = 4;                                    // strips per tile
 constexpr int K2_THREADS = K2_WARPS * 32;
-constexpr int K2_MAX_BLOCK_BITS = 1472;                        // >= 14 + 63*23 = 1463
-constexpr int K2_WIN_WORDS = (K2_THREADS * K2_MAX_BLOCK_BITS) / 32 + 8;
+constexpr int K2_MAX_BLOCK_BITS = 1472;                       // >= 14 + 63*23 = 1463: any tile fits
+constexpr int K2_SMALL_BLOCK_BITS = 512;                      // default window: 64 bytes per block on average
+constexpr int k2_win_words(int block_bits) { return (K2_THREADS * block_bits) / 32 + 8; }
 
 // one record per strip, written by K1
 struct __align__(8) StripRec {
-    uint32_t bits;      // bit cost of the strip's blocks, WITHOUT the DC-difference code of its first block
+    uint32_t bits;      // bit cost of the strip's blocks (an image's first strip: without its first DC symbol)
     int16_t first_dc;   // quantized DC of the strip's first block
     int16_t last_dc;    // quantized DC of the strip's last block
 };
 
 // per-block word written by K1: [15:0] bit offset inside the strip (same convention as
-// StripRec.bits: the first block's DC-difference code not counted), [21:16] index of the last
-// non-zero AC coefficient (0 = none)
+// StripRec.bits), [21:16] index of the last non-zero AC coefficient (0 = none)
 __host__ __device__ __forceinline__ uint32_t blk_pack(uint32_t off, uint32_t last) { return off | (last << 16); }
 
 // device table block (one allocation per encoder): bit-cost LUT for K1, code tables for K2
@@ -54,15 +55,15 @@ constexpr int TBL_DC_CODE = TBL_AC_CODE + 1024;                // uint32 [16]   
 constexpr int TBL_BYTES = TBL_DC_CODE + 64 + 48;               // 17536
 
 constexpr int K2_STAGE_STRIDE = 17;                            // words per lane in the coefficient staging area
-constexpr int K2_SMEM = (K2_WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE) * 4;
+constexpr int k2_smem(int block_bits) { return (k2_win_words(block_bits) + K2_THREADS * K2_STAGE_STRIDE) * 4; }
 
 struct PackArgs {
     const uint8_t *tables;         // device table block (TBL_* offsets)
     const int8_t *coef;            // [count*nb_avail][64] zig-zag int8
     const uint32_t *blkinfo;       // [count*nb_avail]
     const StripRec *strips;        // [count*strips_avail]
-    uint64_t *bit_state;           // [count*tiles] look-back state, bits
-    uint64_t *ff_state;            // [count*tiles] look-back state, stuffed zeros
+    uint64_t *bit_incl;            // bit-offset checkpoints, one per 1024-tile group: [count*groups]
+    uint64_t *ff_agg, *ff_incl;    // grouped look-back state of the stuffed-zero counts: [count*tiles], [count*groups]
     uint8_t *out;                  // stuffed bytes: caller's buffer (count==1) or per-image slots (batch)
     uint64_t out_capacity;         // bytes available per image at `out`
     uint64_t out_slot;             // byte distance between images at `out` (batch), 0 for count==1
@@ -210,165 +211,170 @@ __device__ __forceinline__ uint32_t count_ff_bytes(uint32_t w)
     return __popc(x & 0x01010101u);
 }
 
+// BLOCK_BITS: window capacity per block.  The default instantiation (512) keeps shared memory small
+// (12 CTAs per SM); a tile that does not fit raises ERRBIT_WORKSPACE and the caller re-runs with the
+// worst-case instantiation (1472), selected through jpegb200_encoder_set_bytes_per_block.
+template <int BLOCK_BITS>
 __global__ void __launch_bounds__(K2_THREADS)
 k_scan_pack_stuff(const PackArgs a)
 {
-    extern __shared__ __align__(16) uint32_t win[];          // [K2_WIN_WORDS] bit window, then the staging area
-    uint32_t *stage = win + K2_WIN_WORDS + (threadIdx.x * K2_STAGE_STRIDE);   // this lane's 16 coefficient words
+    constexpr int WIN_WORDS = k2_win_words(BLOCK_BITS);
+    extern __shared__ __align__(16) uint32_t win[];          // [WIN_WORDS] bit window, then the staging area
+    uint32_t *stage = win + WIN_WORDS + (threadIdx.x * K2_STAGE_STRIDE);   // this lane's 16 coefficient words
     __shared__ uint32_t s_ac[256], s_dc[16];
-    __shared__ uint64_t s_strip_base[K2_WARPS];     // window-independent bit offset of each strip (incl. phase)
-    __shared__ uint32_t s_strip_fix[K2_WARPS];      // DC-difference cost of the strip's first block
-    __shared__ uint64_t s_begin, s_end, s_ffexcl;
+    __shared__ uint32_t s_strip_base[K2_WARPS];     // bit offset of each strip inside the tile
     __shared__ uint32_t s_warp[K2_WARPS], s_carry, s_tile_bits;
-    __shared__ uint64_t s_scratch[12];
+    __shared__ uint64_t s_scratch[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, img = blockIdx.y;
-    const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
-    const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
-    const uint32_t nstrips = min((uint32_t)K2_WARPS, a.strips_owned - strip0);
-    const bool last_tile = tile == a.tiles - 1;
-
     for (int i = tid; i < 256; i += K2_THREADS) s_ac[i] = reinterpret_cast<const uint32_t *>(a.tables + TBL_AC_CODE)[i];
     if (tid < 16) s_dc[tid] = reinterpret_cast<const uint32_t *>(a.tables + TBL_DC_CODE)[tid];
+    const uint64_t origin = ((uint64_t)a.bit_phase + 7) >> 3;     // first stream byte this image/stripe owns
+    const int groups = (a.tiles + LB_GROUP - 1) / LB_GROUP;
 
-    // ---- 0. fetch this lane's block before any waiting (loads do not depend on the offsets) ------
-    const uint64_t img_block0 = (uint64_t)img * a.nb_avail;
-    const uint32_t my_strip = strip0 + warp;
-    const bool have = (uint32_t)warp < nstrips && (uint32_t)lane < strip_blocks(my_strip, a.spr, a.bw);
-    uint32_t info = 0;
-    int my_dc = 0;
-    if (have) {
-        const uint32_t brow = my_strip / a.spr, sx = my_strip - brow * a.spr;
-        const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lane;
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + b * 64);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint4 q = src[i];
-            stage[4 * i] = q.x; stage[4 * i + 1] = q.y; stage[4 * i + 2] = q.z; stage[4 * i + 3] = q.w;
-            if (i == 0) my_dc = (int)(int8_t)(q.x & 0xFFu);
-        }
-        info = a.blkinfo[b];
-    }
-    // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
-    // previous strip's last block for lane 0
-    int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
-    if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
+    // persistent CTAs: tile indices are taken in increasing order, so every predecessor of a tile is
+    // either finished or being processed by a resident CTA that never waits on a later tile
+    for (uint64_t t = blockIdx.x; t < (uint64_t)a.tiles * (uint64_t)a.count; t += gridDim.x) {
+        const int img = (int)(t / (uint64_t)a.tiles), tile = (int)(t - (uint64_t)img * a.tiles);
+        const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
+        const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
+        const uint32_t nstrips = min((uint32_t)K2_WARPS, a.strips_owned - strip0);
+        const bool last_tile = tile == a.tiles - 1;
+        uint64_t *bit_incl = a.bit_incl + (uint64_t)img * groups;
+        uint64_t *ff_agg = a.ff_agg + (uint64_t)img * a.tiles, *ff_incl = a.ff_incl + (uint64_t)img * groups;
 
-    // ---- 1. tile bit offset --------------------------------------------------------------
-    if (warp == 0) {
-        uint32_t tot = 0, fix = 0;
-        if ((uint32_t)lane < nstrips) {
-            const StripRec r = recs[strip0 + lane];
-            const int pred = strip0 + lane == 0 ? (int)a.dc_pred0 : (int)recs[strip0 + lane - 1].last_dc;
-            fix = c_dc_len[magnitude_class((int)r.first_dc - pred)];
-            tot = r.bits + fix;
-        }
-        uint32_t incl = tot;
+        // ---- 0. fetch this lane's block before any waiting (loads do not depend on the offsets) ----
+        const uint64_t img_block0 = (uint64_t)img * a.nb_avail;
+        const uint32_t my_strip = strip0 + warp;
+        const bool have = (uint32_t)warp < nstrips && (uint32_t)lane < strip_blocks(my_strip, a.spr, a.bw);
+        uint32_t info = 0;
+        int my_dc = 0;
+        if (have) {
+            const uint32_t brow = my_strip / a.spr, sx = my_strip - brow * a.spr;
+            const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lane;
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + b * 64);
 #pragma unroll
-        for (int o = 1; o < K2_WARPS; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
+            for (int i = 0; i < 4; ++i) {
+                const uint4 q = src[i];
+                stage[4 * i] = q.x; stage[4 * i + 1] = q.y; stage[4 * i + 2] = q.z; stage[4 * i + 3] = q.w;
+                if (i == 0) my_dc = (int)(int8_t)(q.x & 0xFFu);
+            }
+            info = a.blkinfo[b];
         }
-        const uint32_t tile_bits = __shfl_sync(0xffffffffu, incl, K2_WARPS - 1);
-        if (lane == 0) {
-            st_volatile_u64(a.bit_state + (uint64_t)img * a.tiles + tile,
-                            lb_pack(1u, tile == 0 ? LB_PREFIX : LB_AGGREGATE, tile_bits));
-            s_tile_bits = tile_bits;
+        // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
+        // previous strip's last block for lane 0
+        int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+        if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
+
+        // ---- 1. tile bit offset: wait-free ---------------------------------------------------------
+        // K1 left complete per-strip bit counts (only the image's very first DC symbol is missing: its
+        // predictor is a run-time argument), so the offset is a plain sum over the earlier strips of the
+        // tile's 1024-tile group plus the group's checkpoint.
+        const uint32_t fix0 = c_dc_len[magnitude_class((int)recs[0].first_dc - (int)a.dc_pred0)];
+        const int g0 = (tile / LB_GROUP) * LB_GROUP;
+        uint64_t part = 0;
+        for (uint32_t sidx = (uint32_t)g0 * K2_WARPS + tid; sidx < strip0; sidx += K2_THREADS) part += recs[sidx].bits;
+        if (tid == 0) part += g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_scratch[warp] = part;
+        if (warp == 0) {
+            uint32_t tot = (uint32_t)lane < nstrips ? recs[strip0 + lane].bits : 0u;
+            if (tile == 0 && lane == 0) tot += fix0;
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < K2_WARPS; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            if (lane == K2_WARPS - 1) s_tile_bits = incl;
+            if (lane < K2_WARPS) s_strip_base[lane] = incl - tot;
         }
-        if (lane < K2_WARPS) {
-            s_strip_base[lane] = incl - tot;                      // tile-relative for now
-            s_strip_fix[lane] = fix;
-        }
-    }
-    __syncthreads();
-    {
-        uint64_t *state = a.bit_state + (uint64_t)img * a.tiles;
-        const uint64_t excl = lookback_exclusive_cta(state, tile, a.err, s_scratch);
+        __syncthreads();
+        uint64_t bit_excl = 0;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; ++w) bit_excl += s_scratch[w];
+        const uint64_t begin = bit_excl + a.bit_phase, end = begin + s_tile_bits;
         if (tid == 0) {
-            if (tile != 0) st_volatile_u64(state + tile, lb_pack(1u, LB_PREFIX, excl + s_tile_bits));
-            s_begin = excl + a.bit_phase;
-            s_end = excl + a.bit_phase + s_tile_bits;
-            if (last_tile) a.image_bits[img] = excl + s_tile_bits;
+            if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(bit_incl + tile / LB_GROUP, LB_VALID | (bit_excl + s_tile_bits));
+            if (last_tile) a.image_bits[img] = bit_excl + s_tile_bits;
         }
-        if (tid < K2_WARPS) s_strip_base[tid] += excl + a.bit_phase;
-    }
-    __syncthreads();
-    const uint64_t begin = s_begin, end = s_end;
-    const uint64_t w0 = begin >> 5;
-    const uint32_t nwords = (uint32_t)(((end + 31) >> 5) - w0);
-    for (uint32_t i = tid; i < nwords + 2; i += K2_THREADS) win[i] = 0;
-    __syncthreads();
-
-    // ---- 2. pack this tile's blocks --------------------------------------------------------
-    if (have) {
-        const uint64_t off = s_strip_base[warp] + (lane ? s_strip_fix[warp] : 0u) + (info & 0xFFFFu);
-        BitWriter bw;
-        bw.start(win, (uint32_t)(off - (w0 << 5)));
-        encode_block(stage, prev_dc, (int)((info >> 16) & 63u), s_ac, s_dc,
-                     [&](uint32_t v, uint32_t n) { bw.put(v, n); return true; });
-        bw.finish();
-    }
-
-    // ---- 3. complete the last owned byte with the next tile's leading bits (at most 7) -----------
-    // Bytes are owned by the tile that holds their first bit.  Runs concurrently with the packing
-    // above: it only ORs into bits at or after `end`.
-    const uint64_t limit = (end + 7) & ~7ull;                    // first bit NOT owned by this tile
-    if (tid == 0 && (end & 7u) && !(last_tile && a.strips_avail == a.strips_owned)) {
-        uint32_t pos = (uint32_t)(end - (w0 << 5));
-        const uint32_t lim = (uint32_t)(limit - (w0 << 5));
-        uint32_t st = strip0 + nstrips;                          // raster successor of the tile's last block
-        int hprev = (int)recs[st - 1].last_dc;
-        uint32_t lb = 0;
-        for (int n = 0; n < 2 && pos < lim && st < a.strips_avail; ++n) {
-            const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
-            const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) stage[i] = src[i];
-            const uint32_t hinfo = a.blkinfo[b];
-            encode_block(stage, hprev, (int)((hinfo >> 16) & 63u), s_ac, s_dc, [&](uint32_t v, uint32_t nb) {
-                put_clipped(win, pos, lim, v, nb);
-                return pos < lim;
-            });
-            hprev = (int)(int8_t)(stage[0] & 0xFFu);
-            if (++lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
+        const uint64_t w0 = begin >> 5;
+        uint32_t nwords = (uint32_t)(((end + 31) >> 5) - w0);
+        const bool fits = nwords + 2 <= (uint32_t)WIN_WORDS;
+        if (!fits) {                                              // dense tile: needs the large-window instantiation
+            if (tid == 0) atomicOr(a.err, ERRBIT_WORKSPACE);
+            nwords = 0;
         }
-    }
-    __syncthreads();
+        for (uint32_t i = tid; i < nwords + 2; i += K2_THREADS) win[i] = 0;
+        __syncthreads();
 
-    // ---- 4. stuffing ------------------------------------------------------------------------------
-    // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
-    const uint64_t B0 = (begin + 7) >> 3, B1 = (end + 7) >> 3;
-    const uint32_t wb0 = (uint32_t)(B0 - 4 * w0), wb1 = (uint32_t)(B1 - 4 * w0);     // window byte range
-    const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;                        // window word range [wfirst, wlast)
-    auto masked_word = [&](uint32_t i) -> uint32_t {
-        uint32_t v = win[i];
-        const uint32_t lo = i * 4, hi = lo + 4;                   // bytes lo..hi-1 (MSB first)
-        if (lo < wb0) v &= 0xFFFFFFFFu >> (8 * (wb0 - lo));
-        if (hi > wb1) v &= wb1 > lo ? 0xFFFFFFFFu << (8 * (hi - wb1)) : 0u;
-        return v;
-    };
-    uint32_t mine = 0;
-    for (uint32_t i = wfirst + tid; i < wlast; i += K2_THREADS) mine += count_ff_bytes(masked_word(i));
+        // ---- 2. pack this tile's blocks ----------------------------------------------------------
+        if (have && fits) {
+            // K1's strip-local offsets are complete except in the image's first strip (fix0)
+            const uint64_t off = begin + s_strip_base[warp] + (info & 0xFFFFu) + (my_strip == 0 && lane ? fix0 : 0u);
+            BitWriter bw;
+            bw.start(win, (uint32_t)(off - (w0 << 5)));
+            encode_block(stage, prev_dc, (int)((info >> 16) & 63u), s_ac, s_dc,
+                         [&](uint32_t v, uint32_t n) { bw.put(v, n); return true; });
+            bw.finish();
+        }
+
+        // ---- 3. complete the last owned byte with the next tile's leading bits (at most 7) ---------
+        // Bytes are owned by the tile that holds their first bit.  Runs concurrently with the packing
+        // above: it only ORs into bits at or after `end`.
+        const uint64_t limit = (end + 7) & ~7ull;                // first bit NOT owned by this tile
+        if (tid == 0 && fits && (end & 7u) && !(last_tile && a.strips_avail == a.strips_owned)) {
+            uint32_t pos = (uint32_t)(end - (w0 << 5));
+            const uint32_t lim = (uint32_t)(limit - (w0 << 5));
+            uint32_t st = strip0 + nstrips;                      // raster successor of the tile's last block
+            int hprev = (int)recs[st - 1].last_dc;
+            uint32_t lb = 0;
+            for (int n = 0; n < 2 && pos < lim && st < a.strips_avail; ++n) {
+                const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
+                const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane == 0) s_warp[warp] = mine;
-    __syncthreads();
-    {
+                for (int i = 0; i < 16; ++i) stage[i] = src[i];
+                const uint32_t hinfo = a.blkinfo[b];
+                encode_block(stage, hprev, (int)((hinfo >> 16) & 63u), s_ac, s_dc, [&](uint32_t v, uint32_t nb) {
+                    put_clipped(win, pos, lim, v, nb);
+                    return pos < lim;
+                });
+                hprev = (int)(int8_t)(stage[0] & 0xFFu);
+                if (++lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. stuffing ---------------------------------------------------------------------------
+        // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
+        const uint64_t B0 = (begin + 7) >> 3, B1 = fits ? (end + 7) >> 3 : B0;
+        const uint32_t wb0 = (uint32_t)(B0 - 4 * w0), wb1 = (uint32_t)(B1 - 4 * w0);   // window byte range
+        const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;                      // window word range [wfirst, wlast)
+        auto masked_word = [&](uint32_t i) -> uint32_t {
+            uint32_t v = win[i];
+            const uint32_t lo = i * 4, hi = lo + 4;               // bytes lo..hi-1 (MSB first)
+            if (lo < wb0) v &= 0xFFFFFFFFu >> (8 * (wb0 - lo));
+            if (hi > wb1) v &= wb1 > lo ? 0xFFFFFFFFu << (8 * (hi - wb1)) : 0u;
+            return v;
+        };
+        uint32_t mine = 0;
+        for (uint32_t i = wfirst + tid; i < wlast; i += K2_THREADS) mine += count_ff_bytes(masked_word(i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) s_warp[warp] = mine;
+        __syncthreads();
         uint32_t tile_ff = 0;
 #pragma unroll
         for (int w = 0; w < K2_WARPS; ++w) tile_ff += s_warp[w];
-        uint64_t *state = a.ff_state + (uint64_t)img * a.tiles;
-        if (tid == 0) st_volatile_u64(state + tile, lb_pack(1u, tile == 0 ? LB_PREFIX : LB_AGGREGATE, tile_ff));
-        const uint64_t excl = lookback_exclusive_cta(state, tile, a.err, s_scratch);
+        if (tid == 0) st_volatile_u64(ff_agg + tile, LB_VALID | tile_ff);
+        const uint64_t ff_excl = lookback_grouped(ff_agg, ff_incl, tile, a.err, s_scratch);
         if (tid == 0) {
-            if (tile != 0) st_volatile_u64(state + tile, lb_pack(1u, LB_PREFIX, excl + tile_ff));
-            s_ffexcl = excl;
+            if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(ff_incl + tile / LB_GROUP, LB_VALID | (ff_excl + tile_ff));
             s_carry = 0;
             if (last_tile) {
-                const uint64_t origin0 = ((uint64_t)a.bit_phase + 7) >> 3;
-                const uint64_t size = B1 - origin0 + excl + tile_ff;
+                const uint64_t size = B1 - origin + ff_excl + tile_ff;
                 a.image_bytes[img] = size;
                 if (a.count == 1) {
                     a.scan_offsets[0] = 0;
@@ -377,51 +383,51 @@ k_scan_pack_stuff(const PackArgs a)
                 if (size > a.out_capacity) atomicOr(a.err, a.count == 1 ? ERRBIT_OUTPUT : ERRBIT_WORKSPACE);
             }
         }
-    }
-    __syncthreads();
-    const uint64_t origin = ((uint64_t)a.bit_phase + 7) >> 3;     // first stream byte this image/stripe owns
-    uint8_t *out = a.out + (uint64_t)img * a.out_slot;
-    const uint64_t out_base = (B0 - origin) + s_ffexcl;           // output index of window byte wb0
-    for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
-        const uint32_t i = i0 + tid;
-        const uint32_t v = i < wlast ? masked_word(i) : 0u;
-        const uint32_t cnt = count_ff_bytes(v);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        uint32_t before = s_carry + incl - cnt;
-        uint32_t round_total = 0;
+        uint8_t *out = a.out + (uint64_t)img * a.out_slot;
+        const uint64_t out_base = (B0 - origin) + ff_excl;        // output index of window byte wb0
+        for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
+            const uint32_t i = i0 + tid;
+            const uint32_t v = i < wlast ? masked_word(i) : 0u;
+            const uint32_t cnt = count_ff_bytes(v);
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int w = 0; w < K2_WARPS; ++w) {
-            const uint32_t ws = s_warp[w];
-            if (w < warp) before += ws;
-            round_total += ws;
-        }
-        if (i < wlast) {
-            const uint32_t raw = win[i];
-            uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t before = s_carry + incl - cnt;
+            uint32_t round_total = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t wb = i * 4 + k;
-                if (wb >= wb0 && wb < wb1) {
-                    const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
-                    if (pos < a.out_capacity) out[pos] = byte;
-                    ++pos;
-                    if (byte == 0xFF) {                             // huffman.c:29-31
-                        if (pos < a.out_capacity) out[pos] = 0x00;
+            for (int w = 0; w < K2_WARPS; ++w) {
+                const uint32_t ws = s_warp[w];
+                if (w < warp) before += ws;
+                round_total += ws;
+            }
+            if (i < wlast) {
+                const uint32_t raw = win[i];
+                uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t wb = i * 4 + k;
+                    if (wb >= wb0 && wb < wb1) {
+                        const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
+                        if (pos < a.out_capacity) out[pos] = byte;
                         ++pos;
+                        if (byte == 0xFF) {                         // huffman.c:29-31
+                            if (pos < a.out_capacity) out[pos] = 0x00;
+                            ++pos;
+                        }
                     }
                 }
             }
+            __syncthreads();
+            if (tid == 0) s_carry += round_total;
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0) s_carry += round_total;
-        __syncthreads();
+        __syncthreads();                                          // shared state is reused by the next tile
     }
 }
 
