@@ -210,6 +210,10 @@ int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_rgb, int wid
 int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, uint64_t nblocks);
 int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks);
 
+/* Tuning aid: with JPEGB200_K2_TRACE=1 in the environment K2 records 8 phase timestamps (ns) per
+ * tile; this copies them out ([ntiles][8]). */
+int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t ntiles);
+
 /* ---- MCU-row stripes of one image across several GPUs ----------------------
  * Rank r owns block rows [row0, row0+rows) of an image.  d_rgb points at the stripe's first
  * pixel row; stripe_height = pixel rows of the stripe (a multiple of 8 except for the image's

@@ -193,8 +193,13 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     for (int i = threadIdx.x; i < ACLUT_BYTES / 16; i += K1_THREADS)   // ... while the bit-cost table is staged
         cp_async16(aclut + i * 16, tables + TBL_ACLUT + i * 16);
     cp_async_commit();
-    // reset the decoupled look-back state of the scan (K2) and stuffing (K4) kernels that
-    // follow in the stream: keeps a whole encode at four launches and CUDA-graph replayable
+    // Everything above only READS the caller's pixels and constant tables, so it may overlap the
+    // tail of the previous kernel in the stream (programmatic dependent launch).  From here on
+    // this kernel writes buffers the previous encode's K2 may still be reading.
+    pdl_wait();
+    pdl_trigger();
+    // reset the look-back state of the entropy kernel (K2) that follows in the stream: keeps a
+    // whole encode at two launches and CUDA-graph replayable
     for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;
          i += (uint64_t)gridDim.x * K1_THREADS)
         lookback_state[i] = 0;

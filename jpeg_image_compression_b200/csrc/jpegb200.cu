@@ -111,6 +111,24 @@ static void build_tables(HostTables &t)
         }
     }
     t.block[TBL_ACLUT + ACLUT_ROWS * ACLUT_STRIDE] = ac[0x00].len;          // EOB
+    // ready-made AC symbols for K2: [run 0..15][int8 value] -> (code << size | amplitude) << 5 | length
+    // (rle.c:24-35,106-113 + huffman.c:39,164-173).  Value 0 never occurs as a coefficient, so slot
+    // [0][0] carries EOB and the unreachable slot [0][0xF0] (-16 at run 0 is a real value: use its
+    // own entry below) is NOT reused: ZRL lives in [0][0x80] (-128 cannot occur, |q| <= 95).
+    {
+        uint32_t *sym = reinterpret_cast<uint32_t *>(&t.block[TBL_SYM]);
+        for (int run = 0; run < 16; ++run) {
+            for (int b = 1; b < 256; ++b) {
+                const int v = (int)(int8_t)b, sz = bit_length(v);
+                if (sz > 7) continue;
+                const HuffCode hc = ac[(run << 4) | sz];
+                const uint32_t amp = (uint32_t)(v > 0 ? v : v - 1) & ((1u << sz) - 1u);
+                sym[run * 256 + b] = ((((uint32_t)hc.code << sz) | amp) << 5) | (uint32_t)(hc.len + sz);
+            }
+        }
+        sym[0] = ((uint32_t)ac[0x00].code << 5) | ac[0x00].len;            // EOB
+        sym[0x80] = ((uint32_t)ac[0xF0].code << 5) | ac[0xF0].len;         // ZRL
+    }
     memcpy(&t.block[TBL_AC_CODE], t.ac_code, sizeof(t.ac_code));
     memcpy(&t.block[TBL_DC_CODE], t.dc_code, sizeof(t.dc_code));
     memcpy(&t.block[TBL_DC_LEN], t.dc_len, sizeof(t.dc_len));
@@ -148,7 +166,7 @@ struct jpegb200_encoder {
     int dct_mode = 0;
     int bytes_per_block = 24;
     jb::HostTables tables;
-    jb::DeviceBuffer coef, blkinfo, strips, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan;
+    jb::DeviceBuffer coef, blkinfo, strips, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace;
     // last launch
     jb::PackArgs args{};
     jb::Geom geom{};
@@ -156,6 +174,7 @@ struct jpegb200_encoder {
     uint64_t total_blocks = 0;      // blocks K1 produced (all images, incl. stripe halo)
     uint64_t launches = 0;
     int k2_ctas_per_sm[2] = {0, 0};
+    bool pdl = false;               // programmatic dependent launch between K1 and K2 (JPEGB200_PDL=1 enables; measured: no gain)
     bool stripe_ready = false;
     // optional per-kernel timing (cudaEvents on the launching stream)
     bool profiling = false;
@@ -284,6 +303,11 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.count = count;
     a.dc_pred0 = 0;
     a.bit_phase = 0;
+    a.trace = nullptr;
+    if (getenv("JPEGB200_K2_TRACE")) {              // tuning aid: per-tile phase timestamps
+        if ((rc = enc->trace.reserve((uint64_t)tiles * count * 64))) return rc;
+        a.trace = static_cast<unsigned long long *>(enc->trace.ptr);
+    }
     return JPEGB200_OK;
 }
 
@@ -309,6 +333,23 @@ struct TimedLaunch {
     ~TimedLaunch() { if (stop) cudaEventRecord(stop, st); }
 };
 
+// Launch configuration with the programmatic-dependent-launch attribute: the kernel may begin its
+// read-only prologue while the previous kernel in the stream drains (see pdl_wait in common.cuh).
+static thread_local cudaLaunchAttribute g_pdl_attr[1];
+static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    g_pdl_attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = g_pdl_attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+
 // K1: fused block kernel, persistent, two CTAs per SM
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
@@ -317,12 +358,11 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * 2);
     {
         TimedLaunch t(enc, st, KID_BLOCK);
-        k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
-                                                           static_cast<uint32_t *>(enc->blkinfo.ptr),
-                                                           static_cast<StripRec *>(enc->strips.ptr),
-                                                           static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc),
-                                                           enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
-                                                           enc->lookback_words);
+        cudaLaunchConfig_t cfg = pdl_config(dim3((unsigned)grid), dim3(K1_THREADS), K1_SMEM, st, enc->pdl);
+        JB_CUDA(cudaLaunchKernelEx(&cfg, k_fused_blocks, g, static_cast<int8_t *>(enc->coef.ptr),
+                                   static_cast<uint32_t *>(enc->blkinfo.ptr), static_cast<StripRec *>(enc->strips.ptr),
+                                   static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc), enc->dct_mode,
+                                   static_cast<uint64_t *>(enc->lookback.ptr), enc->lookback_words));
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -347,8 +387,9 @@ static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
     const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);
     {
         TimedLaunch t(enc, st, KID_ENTROPY);
-        if (small) k_scan_pack_stuff<K2_SMALL_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
-        else k_scan_pack_stuff<K2_MAX_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
+        cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(K2_THREADS), (size_t)smem, st, enc->pdl);
+        if (small) JB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_pack_stuff<K2_SMALL_BLOCK_BITS>, a));
+        else JB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_pack_stuff<K2_MAX_BLOCK_BITS>, a));
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -432,6 +473,7 @@ extern "C" jpegb200_encoder *jpegb200_encoder_create(int device)
     jpegb200_encoder *enc = new jpegb200_encoder();
     enc->device = device;
     enc->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("JPEGB200_PDL")) enc->pdl = atoi(e) != 0;
     if (upload_tables(enc) != JPEGB200_OK) {
         jpegb200_encoder_destroy(enc);
         return nullptr;
@@ -446,7 +488,7 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
     cudaDeviceSynchronize();
     harvest_events(enc);
     for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->strips, &enc->lookback, &enc->image_bits, &enc->image_bytes,
-                            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan})
+                            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace})
         b->release();
     delete enc;
 }
@@ -549,6 +591,16 @@ extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t
 
 // per-block bit cost, reconstructed from K1's strip-local offsets and strip records exactly the
 // way K2 consumes them
+// tuning aid (JPEGB200_K2_TRACE=1): per-tile phase timestamps of the last K2 launch, [tiles][8] ns
+extern "C" int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t ntiles)
+{
+    if (!enc || !host || !enc->trace.ptr || ntiles * 64 > enc->trace.bytes) return JPEGB200_ERR_ARG;
+    JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    JB_CUDA(cudaMemcpy(host, enc->trace.ptr, ntiles * 64, cudaMemcpyDeviceToHost));
+    return JPEGB200_OK;
+}
+
 extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks)
 {
     if (!enc || !host_bits || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;

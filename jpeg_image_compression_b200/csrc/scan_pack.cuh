@@ -8,7 +8,7 @@
 // K1 leaves, per 32-block strip, a record {bits, first DC, last DC} and per block its bit
 // offset inside the strip, so everything cross-block collapses to two prefix sums:
 //
-//   tile = 4 consecutive strips (<= 128 blocks), one CTA, warp w <-> strip, lane <-> block
+//   tile = 8 consecutive strips (<= 256 blocks), one CTA, warp w <-> strip, lane <-> block
 //   1. warp 0 adds the DC-difference cost of each strip's first block (needs the previous
 //      strip's last DC), sums the tile, publishes the aggregate and obtains the tile's bit
 //      offset by a grouped look-back over the image's earlier tiles (common.cuh);
@@ -28,7 +28,7 @@
 
 namespace jb {
 
-constexpr int K2_WARPS = 4;                                    // strips per tile
+constexpr int K2_WARPS = 8;                                    // strips per tile
 constexpr int K2_THREADS = K2_WARPS * 32;
 constexpr int K2_MAX_BLOCK_BITS = 1472;                       // >= 14 + 63*23 = 1463: any tile fits
 constexpr int K2_SMALL_BLOCK_BITS = 512;                      // default window: 64 bytes per block on average
@@ -52,10 +52,12 @@ constexpr int TBL_ACLUT = 0;                                   // uint8  [63][26
 constexpr int TBL_DC_LEN = 16384;                              // uint8  [16]   DC code length + size  (K1 stages [0, 16400))
 constexpr int TBL_AC_CODE = 16400;                             // uint32 [256]  (code << 8) | len per (run<<4|size)
 constexpr int TBL_DC_CODE = TBL_AC_CODE + 1024;                // uint32 [16]   (code << 8) | len per size class
-constexpr int TBL_BYTES = TBL_DC_CODE + 64 + 48;               // 17536
+constexpr int TBL_SYM = TBL_DC_CODE + 64;                      // uint32 [16][256] ready-made AC symbols, see encode_block
+constexpr int TBL_BYTES = TBL_SYM + 16384 + 32;
 
 constexpr int K2_STAGE_STRIDE = 17;                            // words per lane in the coefficient staging area
-constexpr int k2_smem(int block_bits) { return (k2_win_words(block_bits) + K2_THREADS * K2_STAGE_STRIDE) * 4; }
+constexpr int K2_SYM_WORDS = 16 * 256;                         // AC symbol table staged in shared memory
+constexpr int k2_smem(int block_bits) { return (k2_win_words(block_bits) + K2_THREADS * K2_STAGE_STRIDE + K2_SYM_WORDS) * 4; }
 
 struct PackArgs {
     const uint8_t *tables;         // device table block (TBL_* offsets)
@@ -79,6 +81,7 @@ struct PackArgs {
     int count;
     int16_t dc_pred0;              // DC predictor of the image's first block (0; stripes: previous stripe's last DC)
     uint32_t bit_phase;            // bit offset of the first bit inside byte 0 (0; stripes: global phase & 7)
+    unsigned long long *trace;     // optional [tiles*count][8] phase timestamps (ns), tuning aid; nullptr in production
 };
 
 __device__ __forceinline__ int magnitude_class(int v)          // rle.c:9-22
@@ -93,13 +96,12 @@ __device__ __forceinline__ uint32_t strip_blocks(uint32_t strip_in_image, uint32
     return min(32u, bw - sx * 32u);
 }
 
-// MSB-first bit appender with a 64-bit register accumulator.  The window word that holds the
+// MSB-first bit appender with a 32-bit register accumulator.  The window word that holds the
 // block's first bit and the one that holds its last bit may be shared with the neighbouring
 // blocks (atomicOr); words in between belong to this block alone (plain store).
 struct BitWriter {
     uint32_t *win;
-    uint64_t acc;
-    uint32_t wi, fill;
+    uint32_t acc, wi, fill;
     bool first;
     __device__ __forceinline__ void start(uint32_t *w, uint32_t relbit)
     {
@@ -109,22 +111,22 @@ struct BitWriter {
         acc = 0;
         first = true;
     }
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n)            // n in 1..26, v < 2^n
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n)            // n in 1..27, v < 2^n
     {
-        acc |= (uint64_t)v << (64u - fill - n);
+        const uint32_t vl = v << (32u - n);                                // left-aligned
+        acc |= vl >> fill;
         fill += n;
         if (fill >= 32u) {
-            const uint32_t word = (uint32_t)(acc >> 32);
-            if (first) { atomicOr(win + wi, word); first = false; }
-            else win[wi] = word;
-            acc <<= 32;
+            if (first) { atomicOr(win + wi, acc); first = false; }
+            else win[wi] = acc;
             fill -= 32u;
+            acc = fill ? vl << (n - fill) : 0u;                            // the bits that did not fit
             ++wi;
         }
     }
     __device__ __forceinline__ void finish()
     {
-        if (fill) atomicOr(win + wi, (uint32_t)(acc >> 32));
+        if (fill) atomicOr(win + wi, acc);
     }
 };
 
@@ -156,9 +158,11 @@ __device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
 // memory (zig-zag order, int8).
 // The lane first builds the 63-bit map of its non-zero AC coefficients and then visits only
 // those: the loop trip count is the lane's symbol count, so a warp runs max-over-lanes symbols
-// instead of one divergent branch per coefficient position.
+// instead of one divergent branch per coefficient position.  Each visit is one table look-up:
+// s_sym[run & 15][value & 255] = (Huffman code << size | amplitude bits) << 5 | total length,
+// i.e. huffman.c:164-173 applied to the symbol rle.c:106-113 would have produced.
 template <typename Emit>
-__device__ __forceinline__ void encode_block(const uint32_t *sw, int prev_dc, int last, const uint32_t *s_ac,
+__device__ __forceinline__ void encode_block(const uint32_t *sw, int prev_dc, int last, const uint32_t *s_sym,
                                              const uint32_t *s_dc, Emit emit)
 {
     const uint32_t w0 = sw[0];
@@ -177,29 +181,32 @@ __device__ __forceinline__ void encode_block(const uint32_t *sw, int prev_dc, in
 #pragma unroll
     for (int w = 8; w < 16; ++w)
         if (w <= lastw) mhi |= nonzero_nibble(sw[w]) << (4 * (w - 8));
-    const int8_t *sb = reinterpret_cast<const int8_t *>(sw);
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(sw);
     int prev = 0;                                                 // position of the previous non-zero (0 = DC)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? mhi : mlo;
 #pragma unroll 1
-    while (mlo | mhi) {
-        int k;
-        if (mlo) { k = __ffs((int)mlo) - 1; mlo &= mlo - 1; }
-        else { k = 32 + __ffs((int)mhi) - 1; mhi &= mhi - 1; }
-        const int v = sb[k];
-        int run = k - prev - 1;
-        prev = k;
-        while (run >= 16) {                                                            // ZRL, rle.c:99-103
-            const uint32_t z = s_ac[0xF0];
-            if (!emit(z >> 8, z & 0xFFu)) return;
-            run -= 16;
+        while (m) {
+            const int k = 32 * half + __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint32_t byte = sb[k];
+            int run = k - prev - 1;
+            prev = k;
+            if (run >= 16) {                                                           // ZRL, rle.c:99-103
+                const uint32_t z = s_sym[0x80];           // slot (run 0, value -128: cannot occur) holds the ZRL code
+                do {
+                    if (!emit(z >> 5, z & 31u)) return;
+                    run -= 16;
+                } while (run >= 16);
+            }
+            const uint32_t e = s_sym[(run << 8) | byte];
+            if (!emit(e >> 5, e & 31u)) return;
         }
-        const int sz = magnitude_class(v);
-        const uint32_t hc = s_ac[(run << 4) | sz];
-        const uint32_t amp = (uint32_t)(v > 0 ? v : v - 1) & ((1u << sz) - 1u);
-        if (!emit(((hc >> 8) << sz) | amp, (hc & 0xFFu) + sz)) return;
     }
     if (last < 63) {                                                                   // EOB, rle.c:121-123
-        const uint32_t e = s_ac[0x00];
-        emit(e >> 8, e & 0xFFu);
+        const uint32_t e = s_sym[0];                      // slot (run 0, value 0) holds the EOB code
+        emit(e >> 5, e & 31u);
     }
 }
 
@@ -214,6 +221,14 @@ __device__ __forceinline__ uint32_t count_ff_bytes(uint32_t w)
 // BLOCK_BITS: window capacity per block.  The default instantiation (512) keeps shared memory small
 // (12 CTAs per SM); a tile that does not fit raises ERRBIT_WORKSPACE and the caller re-runs with the
 // worst-case instantiation (1472), selected through jpegb200_encoder_set_bytes_per_block.
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define K2_TRACE(slot) do { if (a.trace && tid == 0) a.trace[t * 8 + (slot)] = globaltimer_ns(); } while (0)
+
 template <int BLOCK_BITS>
 __global__ void __launch_bounds__(K2_THREADS)
 k_scan_pack_stuff(const PackArgs a)
@@ -221,16 +236,20 @@ k_scan_pack_stuff(const PackArgs a)
     constexpr int WIN_WORDS = k2_win_words(BLOCK_BITS);
     extern __shared__ __align__(16) uint32_t win[];          // [WIN_WORDS] bit window, then the staging area
     uint32_t *stage = win + WIN_WORDS + (threadIdx.x * K2_STAGE_STRIDE);   // this lane's 16 coefficient words
-    __shared__ uint32_t s_ac[256], s_dc[16];
+    __shared__ uint32_t s_dc[16];
     __shared__ uint32_t s_strip_base[K2_WARPS];     // bit offset of each strip inside the tile
     __shared__ uint32_t s_warp[K2_WARPS], s_carry, s_tile_bits;
     __shared__ uint64_t s_scratch[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256; i += K2_THREADS) s_ac[i] = reinterpret_cast<const uint32_t *>(a.tables + TBL_AC_CODE)[i];
+    uint32_t *s_sym = win + WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE;
+    for (int i = tid; i < K2_SYM_WORDS / 4; i += K2_THREADS)
+        reinterpret_cast<uint4 *>(s_sym)[i] = reinterpret_cast<const uint4 *>(a.tables + TBL_SYM)[i];
     if (tid < 16) s_dc[tid] = reinterpret_cast<const uint32_t *>(a.tables + TBL_DC_CODE)[tid];
     const uint64_t origin = ((uint64_t)a.bit_phase + 7) >> 3;     // first stream byte this image/stripe owns
     const int groups = (a.tiles + LB_GROUP - 1) / LB_GROUP;
+    pdl_wait();                 // K1's coefficients / records must be complete and visible (tables above are constant)
+    pdl_trigger();              // the next encode's K1 may begin its read-only prologue as SMs drain
 
     // persistent CTAs: tile indices are taken in increasing order, so every predecessor of a tile is
     // either finished or being processed by a resident CTA that never waits on a later tile
@@ -243,6 +262,7 @@ k_scan_pack_stuff(const PackArgs a)
         uint64_t *bit_incl = a.bit_incl + (uint64_t)img * groups;
         uint64_t *ff_agg = a.ff_agg + (uint64_t)img * a.tiles, *ff_incl = a.ff_incl + (uint64_t)img * groups;
 
+        K2_TRACE(0);
         // ---- 0. fetch this lane's block before any waiting (loads do not depend on the offsets) ----
         const uint64_t img_block0 = (uint64_t)img * a.nb_avail;
         const uint32_t my_strip = strip0 + warp;
@@ -266,6 +286,7 @@ k_scan_pack_stuff(const PackArgs a)
         int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
         if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
 
+        K2_TRACE(1);
         // ---- 1. tile bit offset: wait-free ---------------------------------------------------------
         // K1 left complete per-strip bit counts (only the image's very first DC symbol is missing: its
         // predictor is a run-time argument), so the offset is a plain sum over the earlier strips of the
@@ -299,6 +320,7 @@ k_scan_pack_stuff(const PackArgs a)
             if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(bit_incl + tile / LB_GROUP, LB_VALID | (bit_excl + s_tile_bits));
             if (last_tile) a.image_bits[img] = bit_excl + s_tile_bits;
         }
+        K2_TRACE(2);
         const uint64_t w0 = begin >> 5;
         uint32_t nwords = (uint32_t)(((end + 31) >> 5) - w0);
         const bool fits = nwords + 2 <= (uint32_t)WIN_WORDS;
@@ -309,13 +331,14 @@ k_scan_pack_stuff(const PackArgs a)
         for (uint32_t i = tid; i < nwords + 2; i += K2_THREADS) win[i] = 0;
         __syncthreads();
 
+        K2_TRACE(3);
         // ---- 2. pack this tile's blocks ----------------------------------------------------------
         if (have && fits) {
             // K1's strip-local offsets are complete except in the image's first strip (fix0)
             const uint64_t off = begin + s_strip_base[warp] + (info & 0xFFFFu) + (my_strip == 0 && lane ? fix0 : 0u);
             BitWriter bw;
             bw.start(win, (uint32_t)(off - (w0 << 5)));
-            encode_block(stage, prev_dc, (int)((info >> 16) & 63u), s_ac, s_dc,
+            encode_block(stage, prev_dc, (int)((info >> 16) & 63u), s_sym, s_dc,
                          [&](uint32_t v, uint32_t n) { bw.put(v, n); return true; });
             bw.finish();
         }
@@ -337,7 +360,7 @@ k_scan_pack_stuff(const PackArgs a)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) stage[i] = src[i];
                 const uint32_t hinfo = a.blkinfo[b];
-                encode_block(stage, hprev, (int)((hinfo >> 16) & 63u), s_ac, s_dc, [&](uint32_t v, uint32_t nb) {
+                encode_block(stage, hprev, (int)((hinfo >> 16) & 63u), s_sym, s_dc, [&](uint32_t v, uint32_t nb) {
                     put_clipped(win, pos, lim, v, nb);
                     return pos < lim;
                 });
@@ -347,6 +370,7 @@ k_scan_pack_stuff(const PackArgs a)
         }
         __syncthreads();
 
+        K2_TRACE(4);
         // ---- 4. stuffing ---------------------------------------------------------------------------
         // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
         const uint64_t B0 = (begin + 7) >> 3, B1 = fits ? (end + 7) >> 3 : B0;
@@ -368,6 +392,7 @@ k_scan_pack_stuff(const PackArgs a)
         uint32_t tile_ff = 0;
 #pragma unroll
         for (int w = 0; w < K2_WARPS; ++w) tile_ff += s_warp[w];
+        K2_TRACE(5);
         if (tid == 0) st_volatile_u64(ff_agg + tile, LB_VALID | tile_ff);
         const uint64_t ff_excl = lookback_grouped(ff_agg, ff_incl, tile, a.err, s_scratch);
         if (tid == 0) {
@@ -384,6 +409,7 @@ k_scan_pack_stuff(const PackArgs a)
             }
         }
         __syncthreads();
+        K2_TRACE(6);
         uint8_t *out = a.out + (uint64_t)img * a.out_slot;
         const uint64_t out_base = (B0 - origin) + ff_excl;        // output index of window byte wb0
         for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
@@ -427,6 +453,7 @@ k_scan_pack_stuff(const PackArgs a)
             if (tid == 0) s_carry += round_total;
             __syncthreads();
         }
+        K2_TRACE(7);
         __syncthreads();                                          // shared state is reused by the next tile
     }
 }
