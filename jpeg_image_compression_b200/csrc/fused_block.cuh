@@ -38,6 +38,7 @@ namespace jb {
 
 constexpr int K1_WARPS = 8;
 constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr int K1_CTAS_PER_SM = 2;
 constexpr int RAW_PITCH = 784;                       // 768 payload + 16 bytes of alignment slack
 constexpr int RAW_BYTES = 8 * RAW_PITCH;             // 6272
 constexpr int Y_PITCH = 256;
@@ -169,7 +170,7 @@ __device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
     return __uint_as_float(bits) - 8388736.0f;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 2)
+__global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
 k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blkinfo,
                StripRec *__restrict__ strips, const uint8_t *__restrict__ tables,
                unsigned long long *__restrict__ flagged_counter, const int exact_mode,
@@ -208,6 +209,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
 
     uint32_t nflag = 0;
     const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
+    float magic;                                     // 1.5 * 2^23 held in a register: leaves the FFMA's
+    asm("mov.f32 %0, 0f4B400000;" : "=f"(magic));     // constant-bank slot to the quantizer constant c_rk
 
     for (; s < total; s += nwarps) {
         // luma sum of the raster-predecessor block: lane l covers row l/4, columns 2*(l%4) and +1;
@@ -314,8 +317,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                     const float t = x[u][v];
                     const float e = ecls[gclass(u)][gclass(v)];
                     const float rk = c_rk[pos];
-                    hb[j] = __float_as_uint(fmaf(__fadd_rn(t, e), rk, kMagic));
-                    lb[j] = __float_as_uint(fmaf(__fadd_rn(t, -e), rk, kMagic));
+                    hb[j] = __float_as_uint(fmaf(__fadd_rn(t, e), rk, magic));
+                    lb[j] = __float_as_uint(fmaf(__fadd_rn(t, -e), rk, magic));
                 }
                 const uint32_t h = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040u), __byte_perm(hb[2], hb[3], 0x0040u), 0x5410u);
                 const uint32_t l = __byte_perm(__byte_perm(lb[0], lb[1], 0x0040u), __byte_perm(lb[2], lb[3], 0x0040u), 0x5410u);

@@ -350,12 +350,12 @@ static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
     return cfg;
 }
 
-// K1: fused block kernel, persistent, two CTAs per SM
+// K1: fused block kernel, persistent, K1_CTAS_PER_SM CTAs per SM
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
     const Geom &g = enc->geom;
     const uint64_t want = (g.total_strips + K1_WARPS - 1) / K1_WARPS;
-    const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * 2);
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
     {
         TimedLaunch t(enc, st, KID_BLOCK);
         cudaLaunchConfig_t cfg = pdl_config(dim3((unsigned)grid), dim3(K1_THREADS), K1_SMEM, st, enc->pdl);
