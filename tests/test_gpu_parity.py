@@ -338,3 +338,40 @@ def test_dense_tiles_and_ff_bytes(enc, oracle):
     e = jb.DeviceEncoder(0, bytes_per_block=184)
     assert e.encode(rgb) == oracle.encode_scan(rgb)
     e.close()
+
+
+def test_misaligned_base_and_strided_batch(enc, oracle):
+    """Input pointers at any byte alignment and batches with padding between images."""
+    import torch
+    rng = np.random.default_rng(31)
+    w, h, n = 101, 37, 3
+    imgs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    nbytes = w * h * 3
+    for shift, pad in [(1, 0), (3, 5), (7, 13), (0, 64)]:
+        stride = nbytes + pad
+        buf = torch.zeros(shift + n * stride + 64, dtype=torch.uint8, device="cuda")
+        for i in range(n):
+            buf[shift + i * stride: shift + i * stride + nbytes] = torch.from_numpy(imgs[i].reshape(-1)).cuda()
+        view = buf[shift:]
+        scan, offs = enc.encode_device(view, w, h, n, image_stride=stride)
+        enc.status()
+        offs = offs[: n + 1].cpu().numpy()
+        for i in range(n):
+            got = scan[int(offs[i]): int(offs[i + 1])].cpu().numpy().tobytes()
+            assert got == oracle.encode_scan(imgs[i]), (shift, pad, i)
+
+
+def test_extreme_aspect_ratios(enc, oracle):
+    rng = np.random.default_rng(32)
+    for (w, h) in [(1, 700), (700, 1), (8, 4099), (4099, 8), (2049, 9), (15, 15)]:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert enc.encode(rgb) == oracle.encode_scan(rgb), (w, h)
+        smooth = oracle.synth_rgb(w, h, 5, 3)
+        assert enc.encode(smooth) == oracle.encode_scan(smooth), (w, h)
+
+
+def test_many_tiles_cross_group_checkpoint(enc, oracle):
+    """More than 1024 K2 tiles in one image exercises the look-back group checkpoints."""
+    w, h = 256, 8 * 8 * 1030 + 8                      # 1 strip per block row, 8 strips per tile -> 1031 tiles
+    rgb = oracle.synth_rgb(w, h, 77, 30)
+    assert enc.encode(rgb) == oracle.encode_scan(rgb)
