@@ -7,11 +7,12 @@
 //
 // Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels,
 // 6 KB of RGB).  One warp owns a strip:
-//   1. 16-byte cp.async (LDGSTS, L2-only) of the 8 pixel rows into shared memory, at
-//      the rows' natural 16-byte phase (any width / base alignment);
+//   1. TMA bulk copies (cp.async.bulk / UBLKCP, one per pixel row, mbarrier-completed) of the
+//      8 pixel rows into shared memory, at the rows' natural 16-byte phase (any width / base
+//      alignment);
 //   2. cooperative luma pass: 4 pixels per lane-step (funnel-shift realign, PRMT, DP4A),
 //      bytes written to a 256 x 8 Y tile;
-//   3. the next strip's cp.async is issued (the raw tile is free again) so its HBM
+//   3. the next strip's bulk copies are issued (the raw tile is free again) so their HBM
 //      latency overlaps the arithmetic below;
 //   4. one lane per 8x8 block, block entirely in registers: magic-number u8->f32,
 //      scaled even/odd butterfly DCT (rows then columns), quantization by one FFMA per
@@ -95,18 +96,24 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
     return c;
 }
 
-// stage the strip's 8 pixel rows (cp.async, 16 B per lane-step, at most two steps per row)
-__device__ __forceinline__ void strip_issue_loads(const StripCtx &c, uint8_t *raw, int lane)
+// stage the strip's 8 pixel rows: one TMA bulk copy per row (cp.async.bulk -> UBLKCP), issued by one
+// lane and completed through the warp's mbarrier.  Each copy starts at the row's 16-byte-aligned
+// address and covers whole 16-byte chunks, so any width / base alignment works.
+__device__ __forceinline__ void strip_issue_loads(const StripCtx &c, uint8_t *raw, uint64_t *bar, int lane)
 {
+    if (lane == 0) {
+        fence_proxy_async();                             // the tile was just read through the generic proxy
+        uint32_t total = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint32_t mis = (c.mispack >> (4 * r)) & 15u;
-        const uint8_t *a0 = c.row0 + (uint64_t)((uint32_t)min(r, c.rmax) * c.pitch) - mis;
-        const int nch = (int)((mis + 3u * (uint32_t)c.npx + 15u) >> 4);    // <= 49
-        if (lane < nch) cp_async16(raw + r * RAW_PITCH + lane * 16, a0 + lane * 16);
-        if (lane + 32 < nch) cp_async16(raw + r * RAW_PITCH + (lane + 32) * 16, a0 + (lane + 32) * 16);
+        for (int r = 0; r < 8; ++r) total += (((c.mispack >> (4 * r)) & 15u) + 3u * (uint32_t)c.npx + 15u) & ~15u;
+        mbar_expect_tx(bar, total);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t mis = (c.mispack >> (4 * r)) & 15u;
+            const uint8_t *a0 = c.row0 + (uint64_t)((uint32_t)min(r, c.rmax) * c.pitch) - mis;
+            bulk_g2s(raw + r * RAW_PITCH, a0, (mis + 3u * (uint32_t)c.npx + 15u) & ~15u, bar);   // <= 784 bytes
+        }
     }
-    cp_async_commit();
 }
 
 // luma of 4 consecutive pixels held in 3 words: Y = (77R + 150G + 29B) >> 8  (converter.c:51)
@@ -119,19 +126,30 @@ __device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2)
     return __byte_perm(__byte_perm(y0, y1, 0x0051u), __byte_perm(y2, y3, 0x0051u), 0x5410u);
 }
 
+__device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
+{
+    // 0x4B0000xx is 2^23 + xx; subtracting 2^23 + 128 is exact: (float)(xx - 128), converter.c:84
+    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)byte);
+    return __uint_as_float(bits) - 8388736.0f;
+}
+
 // Reference-order evaluation of ONE quantized coefficient (dct.c:65-93,
 // quantization.c:34-36): sequential fp32 sum, two unfused multiplies per term, IEEE
 // divide, round half away from zero.  yblk: the block's Y bytes (pitch Y_PITCH).
 __device__ __noinline__ int exact_quantized(const uint8_t *yblk, int u, int v)
 {
+    float cv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cv[c] = c_ref_cos[c * 8 + v];
     float acc = 0.0f;
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
         const float cu = c_ref_cos[r * 8 + u];
+        const uint2 w = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float pix = (float)((int)yblk[r * Y_PITCH + c] - 128);   // converter.c:84
-            float t = __fmul_rn(pix, cu);
-            t = __fmul_rn(t, c_ref_cos[c * 8 + v]);
+            float t = __fmul_rn(u8_to_centered(c < 4 ? w.x : w.y, c & 3), cu);
+            t = __fmul_rn(t, cv[c]);
             acc = __fadd_rn(acc, t);
         }
     }
@@ -163,13 +181,6 @@ __device__ __forceinline__ void dct8(float &x0, float &x1, float &x2, float &x3,
 // scale class of a frequency index: 0 -> g=1, 1 -> g=cos(pi/8), 2 -> g=cos(pi/4)
 __host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 : (k == 4 ? 2 : 0); }
 
-__device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
-{
-    // 0x4B0000xx is 2^23 + xx; subtracting 2^23 + 128 is exact.
-    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)byte);
-    return __uint_as_float(bits) - 8388736.0f;
-}
-
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
 k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blkinfo,
                StripRec *__restrict__ strips, const uint8_t *__restrict__ tables,
@@ -186,14 +197,22 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     const uint32_t nwarps = gridDim.x * K1_WARPS;
     uint32_t s = blockIdx.x * K1_WARPS + warp;
     const uint32_t total = (uint32_t)g.total_strips;
+    __shared__ __align__(8) uint64_t s_bar[K1_WARPS + 1];      // one mbarrier per warp (pixel tiles) + one for the table
+    uint64_t *bar = &s_bar[warp];
+    if (lane == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) mbar_init(&s_bar[K1_WARPS], 1);
+    mbar_fence_init();
+    __syncthreads();
+    uint32_t phase = 0;
     StripCtx cur;
     if (s < total) {
         cur = strip_ctx(g, s);
-        strip_issue_loads(cur, raw, lane);                       // first strip's pixels are in flight ...
+        strip_issue_loads(cur, raw, bar, lane);                  // first strip's pixels are in flight ...
     }
-    for (int i = threadIdx.x; i < ACLUT_BYTES / 16; i += K1_THREADS)   // ... while the bit-cost table is staged
-        cp_async16(aclut + i * 16, tables + TBL_ACLUT + i * 16);
-    cp_async_commit();
+    if (threadIdx.x == 0) {                                      // ... while the bit-cost table is staged (one 16 KB bulk copy)
+        mbar_expect_tx(&s_bar[K1_WARPS], ACLUT_BYTES);
+        bulk_g2s(aclut, tables + TBL_ACLUT, ACLUT_BYTES, &s_bar[K1_WARPS]);
+    }
     // Everything above only READS the caller's pixels and constant tables, so it may overlap the
     // tail of the previous kernel in the stream (programmatic dependent launch).  From here on
     // this kernel writes buffers the previous encode's K2 may still be reading.
@@ -204,8 +223,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;
          i += (uint64_t)gridDim.x * K1_THREADS)
         lookback_state[i] = 0;
-    cp_async_wait_all();
-    __syncthreads();
+    mbar_wait(&s_bar[K1_WARPS], 0);
 
     uint32_t nflag = 0;
     const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
@@ -221,8 +239,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
             halo_y = ((77u * p0[0] + 150u * p0[1] + 29u * p0[2]) >> 8) + ((77u * p1[0] + 150u * p1[1] + 29u * p1[2]) >> 8);
         }
-        cp_async_wait_all();
-        __syncwarp();
+        mbar_wait(bar, phase);
+        phase ^= 1u;
 
         // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
         if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
@@ -256,7 +274,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         const StripCtx me = cur;
         if (s + nwarps < total) {
             cur = strip_ctx(g, s + nwarps);
-            strip_issue_loads(cur, raw, lane);
+            strip_issue_loads(cur, raw, bar, lane);
         }
 
         // right-edge replication inside the last real block (converter.c:36)
@@ -344,9 +362,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 uint64_t fm = 0;
 #pragma unroll
                 for (int w = 0; w < 16; ++w) {
-                    const uint32_t t = xw[w];
-                    const uint32_t nib = (t & 0xFFu ? 1u : 0u) | (t & 0xFF00u ? 2u : 0u) | (t & 0xFF0000u ? 4u : 0u) | (t & 0xFF000000u ? 8u : 0u);
-                    fm |= (uint64_t)nib << (4 * w);
+                    fm |= (uint64_t)nonzero_nibble(xw[w]) << (4 * w);
                 }
 #pragma unroll 1
                 while (fm) {
