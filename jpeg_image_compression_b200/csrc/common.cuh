@@ -185,7 +185,7 @@ __device__ __forceinline__ uint64_t lookback_grouped(const uint64_t *agg, const 
     const int g0 = (tile / LB_GROUP) * LB_GROUP;
     uint64_t sum = 0;
     if (tid == 0 && g0 > 0) sum = lb_wait(incl + (tile / LB_GROUP) - 1, err);
-    constexpr int BATCH = 8;
+    constexpr int BATCH = 4;                 // 4 x 256 threads = one whole group per pass
     for (int j0 = g0 + tid; j0 < tile; j0 += nthreads * BATCH) {
         uint64_t v[BATCH];
 #pragma unroll
