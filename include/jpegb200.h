@@ -210,6 +210,15 @@ int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_rgb, int wid
 int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, uint64_t nblocks);
 int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks);
 
+/* BMP file image in host memory -> complete JPEG file in host memory (header + scan + EOI), the
+ * opt-in fast path of SURVEY.md section 8f: the BMP's pixel array goes to the device as it is
+ * (bottom-up, BGR, 4-byte padded rows) and the block kernel reads it in place, replacing the host
+ * loader's per-pixel pass (src/io/bmp_handler.c:103-124).  Same acceptance rules as loadBMPImage
+ * (src/io/bmp_handler.c:23-49,68-75,88).  Output bytes equal what saveJPEGGrayscale writes. */
+int jpegb200_encode_bmp_to_jpeg_host(jpegb200_encoder *enc, const uint8_t *bmp, uint64_t bmp_bytes,
+                                     uint8_t *jpeg_out, uint64_t jpeg_capacity, uint64_t *jpeg_bytes,
+                                     int *width, int *height, void *cuda_stream);
+
 /* Tuning aid: with JPEGB200_K2_TRACE=1 in the environment K2 records 8 phase timestamps (ns) per
  * tile; this copies them out ([ntiles][8]). */
 int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t ntiles);

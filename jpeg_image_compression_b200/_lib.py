@@ -73,6 +73,7 @@ EXPORTED_FUNCTIONS = [
     "jpegb200_encoder_set_bytes_per_block", "jpegb200_encode_batch_device", "jpegb200_encoder_status",
     "jpegb200_encoder_stats", "jpegb200_encoder_read_coefficients", "jpegb200_encoder_read_block_bits", "jpegb200_encoder_read_trace",
     "jpegb200_encoder_set_profiling", "jpegb200_encoder_kernel_times", "jpegb200_encode_host",
+    "jpegb200_encode_bmp_to_jpeg_host",
     "jpegb200_stripe_analyze", "jpegb200_stripe_encode", "jpegb200_synth_rgb_device",
 ]
 EXPORTED_DATA = ["std_luminance_quant_tbl", "std_dc_luminance_nrcodes", "std_dc_luminance_values",
@@ -138,6 +139,7 @@ def load_library():
     L.jpegb200_encoder_set_profiling.argtypes = [vp, C.c_int]
     L.jpegb200_encoder_kernel_times.argtypes = [vp, P(C.c_double), P(u64), C.c_int]
     L.jpegb200_encode_host.argtypes = [vp, vp, C.c_int, C.c_int, vp, u64, P(u64), vp]
+    L.jpegb200_encode_bmp_to_jpeg_host.argtypes = [vp, vp, u64, vp, u64, P(u64), P(C.c_int), P(C.c_int), vp]
     L.jpegb200_stripe_analyze.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, P(StripeSummary), vp]
     L.jpegb200_stripe_encode.argtypes = [vp, C.c_int16, u64, vp, u64, P(u64), vp]
     L.jpegb200_synth_rgb_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64, C.c_uint32, C.c_int, vp]

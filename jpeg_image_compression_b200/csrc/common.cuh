@@ -33,8 +33,12 @@ enum : uint32_t {
 
 // geometry of one launch: `count` images of w x h, bw x bh blocks each
 struct Geom {
-    const uint8_t *rgb;
+    const uint8_t *rgb;      // first pixel of the TOP row of image 0
     uint64_t image_stride;
+    int64_t row_pitch;       // bytes from one pixel row to the next one below it: 3*w for BMPImage.data; negative
+                             // (and padded to 4) when the rows of a bottom-up BMP file are read in place
+    uint32_t wt_lo, wt_hi;   // DP4A luma weights for a pixel in bytes 0..2 / 1..3 of a word: (77,150,29) in the
+                             // pixel's channel order (RGB for BMPImage.data, BGR for raw BMP rows)
     int w, h, bw, bh;
     int spr;                 // 32-block strips per block row
     int count;

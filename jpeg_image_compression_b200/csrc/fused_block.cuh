@@ -52,7 +52,7 @@ constexpr int K1_SMEM = ACLUT_BYTES + K1_WARPS * K1_WARP_SMEM;   // 82944
 struct StripCtx {
     const uint8_t *row0;     // first byte of the strip's first pixel row
     uint64_t block0;         // global index of the strip's first block
-    uint32_t pitch;          // bytes per pixel row (3 * width)
+    int64_t pitch;           // bytes from a pixel row to the next (signed: bottom-up BMP rows are walked backwards)
     int rmax;                // last real pixel row of the strip, relative (rows beyond replicate it)
     int npx;                 // real pixels per row in the strip (<= 256)
     int vb;                  // 8x8 blocks in the strip (<= 32)
@@ -70,13 +70,13 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
     const uint32_t brow = rem / (uint32_t)g.spr;
     const uint32_t sx = rem - brow * (uint32_t)g.spr;
     StripCtx c;
-    c.pitch = 3u * (uint32_t)g.w;
-    c.row0 = g.rgb + (uint64_t)img * g.image_stride + (uint64_t)(brow * 8u) * c.pitch + (uint64_t)sx * 768u;
+    c.pitch = g.row_pitch;
+    c.row0 = g.rgb + (uint64_t)img * g.image_stride + (int64_t)(brow * 8u) * c.pitch + (uint64_t)sx * 768u;
     c.block0 = (uint64_t)img * g.blocks_per_image + (uint64_t)brow * (uint32_t)g.bw + sx * 32u;
     c.rmax = min(7, g.h - 1 - (int)(brow * 8u));                          // converter.c:31
     c.npx = min(256, g.w - (int)(sx * 256u));
     c.vb = min(32, g.bw - (int)(sx * 32u));
-    const uint32_t m0 = (uint32_t)((uintptr_t)c.row0 & 15u), step = c.pitch & 15u;
+    const uint32_t m0 = (uint32_t)((uintptr_t)c.row0 & 15u), step = (uint32_t)c.pitch & 15u;
     c.mispack = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) c.mispack |= ((m0 + (uint32_t)min(r, c.rmax) * step) & 15u) << (4 * r);
@@ -86,7 +86,7 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
         c.halo_cmax = 7;
     } else if (brow > 0) {                          // last block of the previous block row
         const int hx0 = (g.bw - 1) * 8;
-        c.halo = c.row0 - (uint64_t)8u * c.pitch + (uint64_t)hx0 * 3u;
+        c.halo = c.row0 - 8 * c.pitch + (int64_t)hx0 * 3;
         c.halo_rmax = 7;
         c.halo_cmax = g.w - 1 - hx0;
     } else {
@@ -110,19 +110,19 @@ __device__ __forceinline__ void strip_issue_loads(const StripCtx &c, uint8_t *ra
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const uint32_t mis = (c.mispack >> (4 * r)) & 15u;
-            const uint8_t *a0 = c.row0 + (uint64_t)((uint32_t)min(r, c.rmax) * c.pitch) - mis;
+            const uint8_t *a0 = c.row0 + (int64_t)min(r, c.rmax) * c.pitch - mis;
             bulk_g2s(raw + r * RAW_PITCH, a0, (mis + 3u * (uint32_t)c.npx + 15u) & ~15u, bar);   // <= 784 bytes
         }
     }
 }
 
 // luma of 4 consecutive pixels held in 3 words: Y = (77R + 150G + 29B) >> 8  (converter.c:51)
-__device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2)
+__device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t wt_lo, uint32_t wt_hi)
 {
-    const uint32_t y0 = __dp4a(w0, 0x001D964Du, 0u);
-    const uint32_t y1 = __dp4a(__byte_perm(w0, w1, 0x0543u), 0x001D964Du, 0u);
-    const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), 0x001D964Du, 0u);
-    const uint32_t y3 = __dp4a(w2, 0x1D964D00u, 0u);
+    const uint32_t y0 = __dp4a(w0, wt_lo, 0u);
+    const uint32_t y1 = __dp4a(__byte_perm(w0, w1, 0x0543u), wt_lo, 0u);
+    const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), wt_lo, 0u);
+    const uint32_t y3 = __dp4a(w2, wt_hi, 0u);
     return __byte_perm(__byte_perm(y0, y1, 0x0051u), __byte_perm(y2, y3, 0x0051u), 0x5410u);
 }
 
@@ -235,9 +235,10 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         // the loads are issued now and consumed after the transform
         uint32_t halo_y = 0;
         if (cur.halo) {
-            const uint8_t *hp = cur.halo + (uint64_t)((uint32_t)min(lane >> 2, cur.halo_rmax) * cur.pitch);
+            const uint8_t *hp = cur.halo + (int64_t)min(lane >> 2, cur.halo_rmax) * cur.pitch;
             const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
-            halo_y = ((77u * p0[0] + 150u * p0[1] + 29u * p0[2]) >> 8) + ((77u * p1[0] + 150u * p1[1] + 29u * p1[2]) >> 8);
+            const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
+            halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -249,8 +250,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             for (int r = 0; r < 8; ++r) {
                 const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
                 uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
-                yo[lane] = luma4(rw[0], rw[1], rw[2]);
-                yo[lane + 32] = luma4(rw[96], rw[97], rw[98]);
+                yo[lane] = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi);
+                yo[lane + 32] = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
             }
         } else {
             // any width / any base alignment: funnel-shift the row to word alignment
@@ -264,7 +265,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                     const uint32_t sh = (mis & 3u) * 8u;
                     const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
                     reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] =
-                        luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh));
+                        luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh), g.wt_lo, g.wt_hi);
                 }
             }
         }

@@ -235,7 +235,8 @@ static uint64_t *misc_offsets(jpegb200_encoder *e)
 // Fill geometry + workspace for `count` images of w x h.  halo_rows > 0 (stripes): the last
 // halo_rows pixel rows belong to the NEXT stripe; K1 transforms them (one extra block row) so
 // that K2 can complete this stripe's last byte, but they are not part of this stripe's stream.
-static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, int count, uint64_t stride, int halo_rows)
+static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, int count, uint64_t stride, int halo_rows,
+                   int64_t row_pitch = 0, bool bgr = false)
 {
     if (!enc || !d_rgb || w <= 0 || h <= 0 || count <= 0 || halo_rows < 0 || halo_rows > 8 || (halo_rows && (h & 7))) {
         g_last_error = "bad argument";
@@ -246,6 +247,9 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     Geom &g = enc->geom;
     g.rgb = d_rgb;
     g.image_stride = stride;
+    g.row_pitch = row_pitch ? row_pitch : 3 * (int64_t)w;
+    g.wt_lo = bgr ? 0x004D961Du : 0x001D964Du;          // bytes (77,150,29,0) resp. (29,150,77,0): converter.c:51
+    g.wt_hi = g.wt_lo << 8;
     g.w = w;
     g.h = h + halo_rows;
     g.bw = (w + 7) / 8;
@@ -737,6 +741,69 @@ extern "C" int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_r
     }
     JB_CUDA(cudaMemcpyAsync(host_scan, d_scan, offs[1], cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));
+    return JPEGB200_OK;
+}
+
+// ---- C ABI: BMP file image in, complete JPEG file out ---------------
+//
+// Opt-in fast path next to the reference-shaped one: the host does NOT run loadBMPImage's per-pixel
+// BGR->RGB / vertical-flip pass (bmp_handler.c:103-124).  The file's pixel array is copied to the
+// device as it is and K1 walks the rows in place (bottom-up => negative row pitch, 4-byte padded
+// rows, BGR channel order => permuted DP4A weights).  Header checks and failure cases are those of
+// loadBMPImage (bmp_handler.c:23-49,68-75,88,104).  The output is the whole file of
+// saveJPEGGrayscale: 328 header bytes (jpeg_handler.c:220-233) + scan + FFD9.
+namespace jb {
+static uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+}
+
+extern "C" int jpegb200_encode_bmp_to_jpeg_host(jpegb200_encoder *enc, const uint8_t *bmp, uint64_t bmp_bytes,
+                                                uint8_t *jpeg_out, uint64_t jpeg_capacity, uint64_t *jpeg_bytes,
+                                                int *width, int *height, void *cuda_stream)
+{
+    if (!enc || !bmp || !jpeg_out || !jpeg_bytes) {
+        g_last_error = "bad argument";
+        return JPEGB200_ERR_ARG;
+    }
+    if (bmp_bytes < 54 || bmp[0] != 'B' || bmp[1] != 'M') { g_last_error = "not a valid BMP file"; return JPEGB200_ERR_ARG; }
+    if ((bmp[28] | (bmp[29] << 8)) != 24) { g_last_error = "only 24-bit BMP images are supported"; return JPEGB200_ERR_ARG; }
+    if (le32(bmp + 30) != 0) { g_last_error = "compressed BMP images are not supported"; return JPEGB200_ERR_ARG; }
+    const int32_t w = (int32_t)le32(bmp + 18);
+    int32_t h = (int32_t)le32(bmp + 22);
+    const bool bottom_up = h >= 0;                                   // bmp_handler.c:68-72
+    if (h < 0) h = -h;
+    if (w <= 0 || h <= 0) { g_last_error = "empty BMP image"; return JPEGB200_ERR_ARG; }
+    const uint64_t pitch = ((uint64_t)w * 3u + 3u) & ~3ull;          // bmp_handler.c:75
+    const uint64_t off = le32(bmp + 10), need = pitch * (uint64_t)h; // bmp_handler.c:88
+    if (off > bmp_bytes || need > bmp_bytes - off) { g_last_error = "insufficient pixel data in BMP file"; return JPEGB200_ERR_ARG; }
+    if (width) *width = w;
+    if (height) *height = h;
+
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    JB_CUDA(cudaSetDevice(enc->device));
+    const uint64_t nb = (uint64_t)((w + 7) / 8) * (uint64_t)((h + 7) / 8);
+    const uint64_t cap = 2 * (nb * (uint64_t)enc->bytes_per_block + 64);
+    int rc = 0;
+    if ((rc = enc->host_in.reserve(need + 64))) return rc;
+    if ((rc = enc->host_scan.reserve(cap + 64))) return rc;
+    uint8_t *d_pix = static_cast<uint8_t *>(enc->host_in.ptr);
+    uint8_t *d_scan = static_cast<uint8_t *>(enc->host_scan.ptr);
+    JB_CUDA(cudaMemcpyAsync(d_pix, bmp + off, need, cudaMemcpyHostToDevice, st));
+    const uint8_t *top = bottom_up ? d_pix + (uint64_t)(h - 1) * pitch : d_pix;
+    if ((rc = prepare(enc, top, w, h, 1, need, 0, bottom_up ? -(int64_t)pitch : (int64_t)pitch, /*bgr=*/true))) return rc;
+    if ((rc = encode_launch(enc, d_scan, cap, misc_offsets(enc), st))) return rc;
+    uint64_t offs[2] = {0, 0};
+    uint32_t err = 0;
+    JB_CUDA(cudaMemcpyAsync(offs, misc_offsets(enc), 16, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaMemcpyAsync(&err, misc_err(enc), 4, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    if (err) return jpegb200_encoder_status(enc, cuda_stream);
+    *jpeg_bytes = 328 + offs[1] + 2;
+    if (*jpeg_bytes > jpeg_capacity) { g_last_error = "JPEG output buffer too small"; return JPEGB200_ERR_OUTPUT; }
+    jpegb200_jfif_header(w, h, jpeg_out);
+    JB_CUDA(cudaMemcpyAsync(jpeg_out + 328, d_scan, offs[1], cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    jpeg_out[328 + offs[1]] = 0xFF;                                  // EOI, jpeg_handler.c:113-117
+    jpeg_out[328 + offs[1] + 1] = 0xD9;
     return JPEGB200_OK;
 }
 

@@ -106,6 +106,23 @@ class DeviceEncoder:
                                             self._stream()), "encode_host")
         return int(n.value)
 
+    def encode_bmp_to_jpeg(self, bmp_bytes, out=None) -> bytes:
+        """BMP file image (bytes / uint8 array / pinned tensor) -> complete JPEG file bytes.  The BMP pixel
+        array is read in place on the device (no host-side BGR->RGB / flip pass)."""
+        if isinstance(bmp_bytes, (bytes, bytearray)):
+            bmp_bytes = np.frombuffer(bytes(bmp_bytes), np.uint8)
+        n_in = bmp_bytes.numel() if hasattr(bmp_bytes, "numel") else bmp_bytes.size
+        ptr = bmp_bytes.data_ptr() if hasattr(bmp_bytes, "data_ptr") else bmp_bytes.ctypes.data
+        if out is None:
+            out = np.empty(n_in + 1024, np.uint8)
+        optr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        cap = out.numel() if hasattr(out, "numel") else out.size
+        n, w, h = C.c_uint64(0), C.c_int(0), C.c_int(0)
+        check(self.lib.jpegb200_encode_bmp_to_jpeg_host(self.handle, ptr, n_in, optr, cap, C.byref(n), C.byref(w), C.byref(h),
+                                                        self._stream()), "encode_bmp_to_jpeg_host")
+        res = out[: n.value]
+        return res.numpy().tobytes() if hasattr(res, "numpy") else res.tobytes()
+
     def set_profiling(self, on: bool):
         check(self.lib.jpegb200_encoder_set_profiling(self.handle, int(on)), "set_profiling")
 

@@ -375,3 +375,48 @@ def test_many_tiles_cross_group_checkpoint(enc, oracle):
     w, h = 256, 8 * 8 * 1030 + 8                      # 1 strip per block row, 8 strips per tile -> 1031 tiles
     rgb = oracle.synth_rgb(w, h, 77, 30)
     assert enc.encode(rgb) == oracle.encode_scan(rgb)
+
+
+def test_bmp_in_place_ingest_equals_reference_path(enc, oracle, golden, tmp_path):
+    """Device-side BMP ingest (bottom-up / top-down rows, padded pitch, BGR, V4/V5 headers) gives the
+    same JPEG file as loadBMPImage + saveJPEGGrayscale of the reference build."""
+    from oracle.oracle import write_bmp
+    rng = np.random.default_rng(12)
+    cases = [(golden["lena_crop256/rgb"], False, 40), (golden["greenland_corner250x205/rgb"], False, 40),
+             (golden["offset_crop320x213/rgb"], False, 124), (golden["one_pixel/rgb"], True, 40),
+             (rng.integers(0, 256, (37, 101, 3), dtype=np.uint8), True, 108), (oracle.synth_rgb(1283, 725, 9, 20), False, 40),
+             (rng.integers(0, 256, (9, 7, 3), dtype=np.uint8), False, 40), (oracle.synth_rgb(258, 64, 2, 30), True, 40)]
+    for i, (rgb, top_down, hsz) in enumerate(cases):
+        p = str(tmp_path / f"c{i}.bmp")
+        write_bmp(p, rgb, top_down=top_down, header_size=hsz)
+        got = enc.encode_bmp_to_jpeg(open(p, "rb").read())
+        assert got == oracle.encode_file_bytes(rgb), (i, rgb.shape, top_down, hsz)
+    for name in golden["bmp_names"]:
+        data = open(os.path.join(ROOT, "tests", "golden", "bmp", f"{name}.bmp"), "rb").read()
+        assert enc.encode_bmp_to_jpeg(data) == oracle.encode_file_bytes(golden[f"bmp/{name}"]), name
+    # rejected like the reference loader: wrong magic, 8-bit, compressed, truncated
+    bad = bytearray(open(str(tmp_path / "c0.bmp"), "rb").read())
+    for patch in ((0, b"P"), (28, b"\x08"), (30, b"\x01")):
+        b2 = bytearray(bad)
+        b2[patch[0]:patch[0] + 1] = patch[1]
+        with pytest.raises(jb.JpegB200Error):
+            enc.encode_bmp_to_jpeg(bytes(b2))
+    with pytest.raises(jb.JpegB200Error):
+        enc.encode_bmp_to_jpeg(bytes(bad[:-5]))
+
+
+def test_batch_cli(golden, oracle, tmp_path):
+    from oracle.oracle import write_bmp
+    app = os.path.join(ROOT, "jpeg_image_compression_b200", "jpeg_compression_batch")
+    names = ["lena_crop256", "greenland_corner250x205", "noise64", "one_pixel", "synth_200x120_amp20"]
+    ins = []
+    for n in names:
+        p = str(tmp_path / f"{n}.bmp")
+        write_bmp(p, golden[f"{n}/rgb"], top_down=(n == "noise64"))
+        ins.append(p)
+    out_dir = tmp_path / "out"
+    out_dir.mkdir()
+    r = subprocess.run([app, str(out_dir)] + ins + [str(tmp_path / "missing.bmp")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Encoded 5 of 6 files" in r.stdout and "Unable to open file" in r.stderr
+    for n in names:
+        assert open(out_dir / f"{n}.jpg", "rb").read() == golden[f"{n}/file"].tobytes(), n

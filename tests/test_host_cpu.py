@@ -139,3 +139,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".c", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_batch_cli_usage(lib):
+    app = os.path.join(ROOT, "jpeg_image_compression_b200", "jpeg_compression_batch")
+    r = subprocess.run([app], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr
