@@ -28,6 +28,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (printed on stdout at VERSION level) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "Mpixel/s BMP->JPEG encode (natural_c hot path)"
 UNIT = "Mpixel/s"

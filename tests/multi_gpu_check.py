@@ -12,6 +12,8 @@ import json
 import os
 import sys
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 import torch
 import torch.distributed as dist
 
