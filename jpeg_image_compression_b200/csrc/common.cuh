@@ -20,8 +20,16 @@ __constant__ uint8_t c_dc_len[16];    // DC Huffman code length + size, per size
 __constant__ uint32_t c_dc_code[16];  // (code << 8) | len, per size class
 __constant__ uint32_t c_ac_code[256]; // (code << 8) | len, per (run<<4|size) symbol
 
-// guard-band factor: |s_ref - g*T| <= kGamma * sum|p|; the derivation in DESIGN.md gives 102.8 * 2^-24 = 6.13e-6
+// Guard half-width of the quantization bracket, in units of the un-scaled DCT sum s:
+//   |s_ref - g*T|  <=  min( kGamma * A ,  kGammaA * A + kGammaC * Ac + kGamma0 )
+// A = sum|p| over the block, Ac = sum|p - c| with c = round(mean p).  The second form separates the part of
+// the reference's rounding error that scales with the block's DC level (only its running partial sums see
+// it) from everything that only sees the deviations from the mean.  With u = 2^-24:
+//   kGamma = 6.5e-6 (>= 102.8 u), kGammaA >= 16.97 u, kGammaC >= 100.67 u, kGamma0 >= 479 u.
 constexpr float kGamma = 6.5e-6f;
+constexpr float kGammaA = 1.0431e-6f;     // 17.5 u
+constexpr float kGammaC = 6.1394e-6f;     // 103 u
+constexpr float kGamma0 = 2.9803e-5f;     // 500 u
 constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: fmaf(x, r, kMagic) rounds x*r to nearest-even integer
 
 // error word bits (device -> host)

@@ -310,8 +310,20 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             for (int c = 0; c < 8; ++c)
                 dct8(x[0][c], x[1][c], x[2][c], x[3][c], x[4][c], x[5][c], x[6][c], x[7][c]);
 
+            // Ac = sum |Y - m|, m = the block's rounded mean luma (from the exact DC sum)
+            uint32_t absmean = 0;
+            {
+                const int mean = (int)rintf(x[0][0] * 0.015625f) + 128;
+                const uint32_t m4 = (uint32_t)mean * 0x01010101u;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
+                    absmean = __vsadu4(v.x, m4) + absmean;
+                    absmean = __vsadu4(v.y, m4) + absmean;
+                }
+            }
             // guard half-widths in T units for the 6 scale-class pairs
-            const float eb = (float)absdev * kGamma;
+            const float eb = fminf((float)absdev * kGamma, fmaf((float)absdev, kGammaA, fmaf((float)absmean, kGammaC, kGamma0)));
             float ecls[3][3];
             {
                 constexpr float IG[3] = {1.0f, 1.0823922002923940f, 1.4142135623730951f};   // 1/g, rounded up

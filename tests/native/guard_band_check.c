@@ -2,9 +2,12 @@
  * order and FMA placement as jpeg_image_compression_b200/csrc/fused_block.cuh:dct8) against the
  * reference-order sum (oracle/jpeg_oracle.c:orc_fdct_block without the final scale).
  *
- * Prints  max over blocks and coefficients of |s_ref - g*T| / sum|p|  which must stay below
- * kGamma = 1e-5 (the guard half-width used on the device), for several input families.
- * usage: guard_band_check <nblocks> <seed>
+ * Prints two numbers:
+ *   max over blocks and coefficients of |s_ref - g*T| / sum|p|           (must stay below kGamma)
+ *   max of |s_ref - g*T| / (kGammaA*A + kGammaC*Ac + kGamma0)             (must stay below 1)
+ * with A = sum|p|, Ac = sum|p - round(mean p)| -- the two guard half-widths used on the device --
+ * for several input families.
+ * usage: guard_band_check <nblocks> <seed> <kGammaA> <kGammaC> <kGamma0>
  */
 #include <math.h>
 #include <stdint.h>
@@ -51,10 +54,11 @@ int main(int argc, char **argv)
     const long nblocks = argc > 1 ? atol(argv[1]) : 100000;
     rng_state = argc > 2 ? (uint64_t)atoll(argv[2]) : 1;
     const double g[8] = {1.0, 1.0, cos(M_PI / 8), 1.0, cos(M_PI / 4), 1.0, cos(M_PI / 8), 1.0};
-    double worst = 0.0;
+    double worst = 0.0, worst2 = 0.0;
+    const double gA = argc > 3 ? atof(argv[3]) : 1.0431e-6, gC = argc > 4 ? atof(argv[4]) : 6.1394e-6, g0 = argc > 5 ? atof(argv[5]) : 2.9803e-5;
     for (long n = 0; n < nblocks; ++n) {
         int p[8][8];
-        const int family = (int)(n % 5);
+        const int family = (int)(n % 8);
         const int base = (int)(rnd() % 256), amp = 1 + (int)(rnd() % 128);
         for (int r = 0; r < 8; ++r)
             for (int c = 0; c < 8; ++c) {
@@ -64,15 +68,21 @@ int main(int argc, char **argv)
                 case 1: v = base + (int)(rnd() % (2 * amp + 1)) - amp; break;             /* flat + noise   */
                 case 2: v = (rnd() & 1) ? 255 : 0; break;                                 /* saturated      */
                 case 3: v = base + (r * amp) / 8 + (c * amp) / 5; break;                  /* ramp           */
-                default: v = ((r + c) & 1) ? base : 255 - base; break;                    /* checker        */
+                case 4: v = ((r + c) & 1) ? base : 255 - base; break;                     /* checker        */
+                case 5: v = base; break;                                                  /* constant: only the DC level */
+                case 6: v = base + (int)(rnd() % 3) - 1; break;                           /* DC level +-1   */
+                default: v = (c < 4 ? base : 255 - base) + (int)(rnd() % 5) - 2; break;   /* vertical edge  */
                 }
                 v = v < 0 ? 0 : (v > 255 ? 255 : v);
                 p[r][c] = v - 128;
             }
-        double A = 0;
+        double A = 0, Ac = 0, sum = 0;
         float x[8][8];
         for (int r = 0; r < 8; ++r)
-            for (int c = 0; c < 8; ++c) { x[r][c] = (float)p[r][c]; A += abs(p[r][c]); }
+            for (int c = 0; c < 8; ++c) { x[r][c] = (float)p[r][c]; A += abs(p[r][c]); sum += p[r][c]; }
+        const int mean = (int)rint(sum / 64.0);
+        for (int r = 0; r < 8; ++r)
+            for (int c = 0; c < 8; ++c) Ac += abs(p[r][c] - mean);
         for (int r = 0; r < 8; ++r) dct8(&x[r][0], &x[r][1], &x[r][2], &x[r][3], &x[r][4], &x[r][5], &x[r][6], &x[r][7]);
         for (int c = 0; c < 8; ++c) dct8(&x[0][c], &x[1][c], &x[2][c], &x[3][c], &x[4][c], &x[5][c], &x[6][c], &x[7][c]);
         if (A == 0) continue;
@@ -86,10 +96,12 @@ int main(int argc, char **argv)
                         t = t * k_cos[c][v];
                         acc = acc + t;
                     }
-                const double err = fabs((double)acc - g[u] * g[v] * (double)x[u][v]) / A;
-                if (err > worst) worst = err;
+                if (u == 0 && v == 0) continue;             /* DC is handled exactly on the device */
+                const double diff = fabs((double)acc - g[u] * g[v] * (double)x[u][v]);
+                if (diff / A > worst) worst = diff / A;
+                if (diff / (gA * A + gC * Ac + g0) > worst2) worst2 = diff / (gA * A + gC * Ac + g0);
             }
     }
-    printf("%.6e\n", worst);
+    printf("%.6e %.6e\n", worst, worst2);
     return 0;
 }

@@ -14,10 +14,15 @@ def test_guard_band_margin(tmp_path):
     exe = str(tmp_path / "guard_band_check")
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", exe,
                     os.path.join(ROOT, "tests", "native", "guard_band_check.c"), "-lm"], check=True)
-    worst = float(subprocess.run([exe, "150000", "11"], check=True, capture_output=True, text=True).stdout)
     cuh = open(os.path.join(ROOT, "jpeg_image_compression_b200", "csrc", "common.cuh")).read()
-    gamma = float(re.search(r"kGamma\s*=\s*([0-9.eE+-]+)f", cuh).group(1))
+
+    def const(name):
+        return float(re.search(name + r"\s*=\s*([0-9.eE+-]+)f", cuh).group(1))
+    gamma, ga, gc, g0 = const("kGamma"), const("kGammaA"), const("kGammaC"), const("kGamma0")
+    out = subprocess.run([exe, "150000", "11", str(ga), str(gc), str(g0)], check=True, capture_output=True, text=True).stdout
+    worst, worst_refined = (float(v) for v in out.split())
     assert 0 < worst < gamma / 5, (worst, gamma)
+    assert 0 < worst_refined < 0.5, worst_refined           # refined (mean-separated) bound: at least 2x margin
 
 
 def test_emulated_butterfly_matches_device_source():
