@@ -500,7 +500,9 @@ k_layout(const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ scan_o
     }
 }
 
-// batch mode: move every image's stuffed bytes from its slot to its final offset
+// batch mode: move every image's stuffed bytes from its (16-byte aligned) slot to its final, arbitrarily
+// aligned offset.  Destination-aligned 32-bit stores; the source is read as aligned words and realigned
+// with a funnel shift; the few head / tail bytes are copied one by one.
 __global__ void __launch_bounds__(256)
 k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const uint64_t *__restrict__ image_bytes,
           const uint64_t *__restrict__ scan_offsets, uint8_t *__restrict__ scan, const uint64_t scan_capacity)
@@ -509,13 +511,16 @@ k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const u
     const uint64_t n = image_bytes[img], dst0 = scan_offsets[img];
     if (dst0 + n > scan_capacity) return;                        // flagged by k_layout
     const uint8_t *src = slots + (uint64_t)img * slot_stride;
-    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += (uint64_t)gridDim.x * blockDim.x * 16) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(src + i);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (i + k < n) scan[dst0 + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-    }
+    uint8_t *dst = scan + dst0;
+    const uint64_t head = min(n, (uint64_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));   // bytes up to dst alignment
+    const uint64_t nwords = (n - head) >> 2, tail0 = head + nwords * 4;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    if (tid < head) dst[tid] = src[tid];
+    if (tid < n - tail0) dst[tail0 + tid] = src[tail0 + tid];
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t sh = (uint32_t)head * 8u;                     // src word phase relative to dst words (head < 4)
+    for (uint64_t j = tid; j < nwords; j += nthreads) d32[j] = __funnelshift_r(s32[j], s32[j + 1], sh);
 }
 
 }  // namespace jb
