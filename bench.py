@@ -28,9 +28,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (printed on stdout at VERSION level) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry exactly ONE JSON line, but native libraries (e.g. NCCL's version banner) write to
+# file descriptor 1 too: park the real stdout, point fd 1 at stderr for the whole run, and emit the
+# result line on the parked descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "Mpixel/s BMP->JPEG encode (natural_c hot path)"
 UNIT = "Mpixel/s"
@@ -173,7 +180,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -423,7 +430,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for e in encs:
         e.close()
     if world > 1:
