@@ -54,13 +54,6 @@ struct Geom {
     uint64_t total_strips;
 };
 
-// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
-// serialization attribute may start while its predecessor in the stream is still draining;
-// pdl_wait() blocks until the predecessor has completed and its writes are visible (a no-op for
-// ordinary launches), pdl_trigger() lets the successor's CTAs be scheduled as resources free up.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);

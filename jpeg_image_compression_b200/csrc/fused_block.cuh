@@ -213,11 +213,6 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         mbar_expect_tx(&s_bar[K1_WARPS], ACLUT_BYTES);
         bulk_g2s(aclut, tables + TBL_ACLUT, ACLUT_BYTES, &s_bar[K1_WARPS]);
     }
-    // Everything above only READS the caller's pixels and constant tables, so it may overlap the
-    // tail of the previous kernel in the stream (programmatic dependent launch).  From here on
-    // this kernel writes buffers the previous encode's K2 may still be reading.
-    pdl_wait();
-    pdl_trigger();
     // reset the look-back state of the entropy kernel (K2) that follows in the stream: keeps a
     // whole encode at two launches and CUDA-graph replayable
     for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;

@@ -174,7 +174,6 @@ struct jpegb200_encoder {
     uint64_t total_blocks = 0;      // blocks K1 produced (all images, incl. stripe halo)
     uint64_t launches = 0;
     int k2_ctas_per_sm[2] = {0, 0};
-    bool pdl = false;               // programmatic dependent launch between K1 and K2 (JPEGB200_PDL=1 enables; measured: no gain)
     bool stripe_ready = false;
     // optional per-kernel timing (cudaEvents on the launching stream)
     bool profiling = false;
@@ -275,7 +274,9 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     // grouped look-back state of K2 (aggregate per tile + inclusive prefix per 1024-tile group), once
     // for the bit offsets and once for the stuffed-zero counts; contiguous, cleared by K1's prologue
     const int groups = (tiles + LB_GROUP - 1) / LB_GROUP;
-    enc->lookback_words = ((uint64_t)tiles + 2ull * (uint64_t)groups) * (uint64_t)count;
+    // ... followed by K2's tile counter in a 128-byte line of its own (it is hammered with atomics)
+    const uint64_t state_words = (((uint64_t)tiles + 2ull * (uint64_t)groups) * (uint64_t)count + 15) & ~15ull;
+    enc->lookback_words = state_words + 16;
     if ((rc = enc->lookback.reserve(enc->lookback_words * 8))) return rc;
     if ((rc = enc->image_bits.reserve((uint64_t)count * 8))) return rc;
     if ((rc = enc->image_bytes.reserve((uint64_t)count * 8))) return rc;
@@ -291,6 +292,7 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.bit_incl = static_cast<uint64_t *>(enc->lookback.ptr);
     a.ff_agg = a.bit_incl + (uint64_t)groups * (uint64_t)count;
     a.ff_incl = a.ff_agg + (uint64_t)tiles * (uint64_t)count;
+    a.tile_counter = reinterpret_cast<unsigned long long *>(static_cast<uint64_t *>(enc->lookback.ptr) + state_words);
     a.out = count > 1 ? static_cast<uint8_t *>(enc->slots.ptr) : nullptr;
     a.out_capacity = count > 1 ? slot : 0;
     a.out_slot = count > 1 ? slot : 0;
@@ -337,23 +339,6 @@ struct TimedLaunch {
     ~TimedLaunch() { if (stop) cudaEventRecord(stop, st); }
 };
 
-// Launch configuration with the programmatic-dependent-launch attribute: the kernel may begin its
-// read-only prologue while the previous kernel in the stream drains (see pdl_wait in common.cuh).
-static thread_local cudaLaunchAttribute g_pdl_attr[1];
-static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    g_pdl_attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-    cfg.attrs = g_pdl_attr;
-    cfg.numAttrs = 1;
-    return cfg;
-}
-
 // K1: fused block kernel, persistent, K1_CTAS_PER_SM CTAs per SM
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
@@ -362,11 +347,12 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
     {
         TimedLaunch t(enc, st, KID_BLOCK);
-        cudaLaunchConfig_t cfg = pdl_config(dim3((unsigned)grid), dim3(K1_THREADS), K1_SMEM, st, enc->pdl);
-        JB_CUDA(cudaLaunchKernelEx(&cfg, k_fused_blocks, g, static_cast<int8_t *>(enc->coef.ptr),
-                                   static_cast<uint32_t *>(enc->blkinfo.ptr), static_cast<StripRec *>(enc->strips.ptr),
-                                   static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc), enc->dct_mode,
-                                   static_cast<uint64_t *>(enc->lookback.ptr), enc->lookback_words));
+        k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
+                                                           static_cast<uint32_t *>(enc->blkinfo.ptr),
+                                                           static_cast<StripRec *>(enc->strips.ptr),
+                                                           static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc),
+                                                           enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
+                                                           enc->lookback_words);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -389,11 +375,11 @@ static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
     }
     const uint64_t total = (uint64_t)a.tiles * (uint64_t)a.count;
     const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);
+    enc->args.dynamic_tiles = total > grid ? 1 : 0;            // more tiles than one wave: persistent CTAs + ticket counter
     {
         TimedLaunch t(enc, st, KID_ENTROPY);
-        cudaLaunchConfig_t cfg = pdl_config(dim3(grid), dim3(K2_THREADS), (size_t)smem, st, enc->pdl);
-        if (small) JB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_pack_stuff<K2_SMALL_BLOCK_BITS>, a));
-        else JB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_pack_stuff<K2_MAX_BLOCK_BITS>, a));
+        if (small) k_scan_pack_stuff<K2_SMALL_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
+        else k_scan_pack_stuff<K2_MAX_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -477,7 +463,6 @@ extern "C" jpegb200_encoder *jpegb200_encoder_create(int device)
     jpegb200_encoder *enc = new jpegb200_encoder();
     enc->device = device;
     enc->sm_count = prop.multiProcessorCount;
-    if (const char *e = getenv("JPEGB200_PDL")) enc->pdl = atoi(e) != 0;
     if (upload_tables(enc) != JPEGB200_OK) {
         jpegb200_encoder_destroy(enc);
         return nullptr;

@@ -66,6 +66,8 @@ struct PackArgs {
     const StripRec *strips;        // [count*strips_avail]
     uint64_t *bit_incl;            // bit-offset checkpoints, one per 1024-tile group: [count*groups]
     uint64_t *ff_agg, *ff_incl;    // grouped look-back state of the stuffed-zero counts: [count*tiles], [count*groups]
+    unsigned long long *tile_counter;   // next tile to hand out (cleared together with the look-back state)
+    int dynamic_tiles;             // 0: one tile per CTA (tile = blockIdx.x); 1: persistent CTAs draw tiles from tile_counter
     uint8_t *out;                  // stuffed bytes: caller's buffer (count==1) or per-image slots (batch)
     uint64_t out_capacity;         // bytes available per image at `out`
     uint64_t out_slot;             // byte distance between images at `out` (batch), 0 for count==1
@@ -242,18 +244,25 @@ k_scan_pack_stuff(const PackArgs a)
     __shared__ uint64_t s_scratch[9];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned long long s_next_tile;
+    if (tid == 0) s_next_tile = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : (unsigned long long)blockIdx.x;
     uint32_t *s_sym = win + WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE;
     for (int i = tid; i < K2_SYM_WORDS / 4; i += K2_THREADS)
         reinterpret_cast<uint4 *>(s_sym)[i] = reinterpret_cast<const uint4 *>(a.tables + TBL_SYM)[i];
     if (tid < 16) s_dc[tid] = reinterpret_cast<const uint32_t *>(a.tables + TBL_DC_CODE)[tid];
     const uint64_t origin = ((uint64_t)a.bit_phase + 7) >> 3;     // first stream byte this image/stripe owns
     const int groups = (a.tiles + LB_GROUP - 1) / LB_GROUP;
-    pdl_wait();                 // K1's coefficients / records must be complete and visible (tables above are constant)
-    pdl_trigger();              // the next encode's K1 may begin its read-only prologue as SMs drain
 
-    // persistent CTAs: tile indices are taken in increasing order, so every predecessor of a tile is
-    // either finished or being processed by a resident CTA that never waits on a later tile
-    for (uint64_t t = blockIdx.x; t < (uint64_t)a.tiles * (uint64_t)a.count; t += gridDim.x) {
+    // Tiles wait on their predecessors (look-backs), so a tile must never be owned by a CTA that is not
+    // running yet.  If all tiles fit in one wave the launch has one CTA per tile (tile = blockIdx.x: CTAs
+    // are dispatched in index order).  Otherwise persistent CTAs draw tiles from an atomic counter,
+    // strictly in increasing order and only once the CTA runs: every predecessor of a tile is then finished
+    // or in the hands of a running CTA that never waits on a later tile -- no deadlock even when only part
+    // of the grid is resident (e.g. next to another stream's kernels).
+    for (;;) {
+        __syncthreads();
+        const uint64_t t = s_next_tile;
+        if (t >= (uint64_t)a.tiles * (uint64_t)a.count) break;
         const int img = (int)(t / (uint64_t)a.tiles), tile = (int)(t - (uint64_t)img * a.tiles);
         const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
         const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
@@ -395,9 +404,13 @@ k_scan_pack_stuff(const PackArgs a)
         K2_TRACE(5);
         if (tid == 0) st_volatile_u64(ff_agg + tile, LB_VALID | tile_ff);
         const uint64_t ff_excl = lookback_grouped(ff_agg, ff_incl, tile, a.err, s_scratch);
+        unsigned long long ticket = ~0ull;
         if (tid == 0) {
             if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(ff_incl + tile / LB_GROUP, LB_VALID | (ff_excl + tile_ff));
             s_carry = 0;
+            // next ticket, kept in a register until after the write-out so that its round trip overlaps
+            // it (static launches process exactly one tile)
+            ticket = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : ~0ull;
             if (last_tile) {
                 const uint64_t size = B1 - origin + ff_excl + tile_ff;
                 a.image_bytes[img] = size;
@@ -454,6 +467,7 @@ k_scan_pack_stuff(const PackArgs a)
             __syncthreads();
         }
         K2_TRACE(7);
+        if (tid == 0) s_next_tile = ticket;
         __syncthreads();                                          // shared state is reused by the next tile
     }
 }

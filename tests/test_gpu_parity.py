@@ -420,3 +420,32 @@ def test_batch_cli(golden, oracle, tmp_path):
     assert r.returncode == 1 and "Encoded 5 of 6 files" in r.stdout and "Unable to open file" in r.stderr
     for n in names:
         assert open(out_dir / f"{n}.jpg", "rb").read() == golden[f"{n}/file"].tobytes(), n
+
+
+def test_two_streams_many_tiles_no_deadlock(synth_hashes):
+    """Two encoder handles on two streams, images with more K2 tiles than resident CTAs: the fused
+    entropy kernels of both streams run side by side, each only partly resident.  Tiles are handed out
+    by an atomic counter, so neither grid can wait on a tile that has not been taken by a running CTA."""
+    import torch
+    e = synth_hashes["7680x4320_seed1_amp20"]
+    encs = [jb.DeviceEncoder(0), jb.DeviceEncoder(0)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    d = encs[0].synth(e["w"], e["h"], 1, e["seed"], e["amp"])
+    torch.cuda.synchronize()
+    outs = []
+    for k in range(6):
+        for enc_, st in zip(encs, streams):
+            with torch.cuda.stream(st):
+                cap = enc_.scan_capacity(e["w"], e["h"], 1)
+                s = torch.empty(cap, dtype=torch.uint8, device="cuda")
+                o = torch.zeros(2, dtype=torch.int64, device="cuda")
+                enc_.encode_device(d, e["w"], e["h"], 1, scan=s, offsets=o)
+                outs.append((s, o))
+    torch.cuda.synchronize()
+    for enc_ in encs:
+        enc_.status()
+    for s, o in outs:
+        n = int(o[1].item())
+        assert n == e["scan_bytes"] and hashlib.sha256(s[:n].cpu().numpy().tobytes()).hexdigest() == e["scan_sha256"]
+    for enc_ in encs:
+        enc_.close()
