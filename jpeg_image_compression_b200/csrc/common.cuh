@@ -67,6 +67,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ---- TMA bulk copies (cp.async.bulk -> UBLKCP) completed through an mbarrier ------------------
+// nanosecond wall clock shared by all SMs (tuning aids only)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");

@@ -62,13 +62,40 @@ struct StripCtx {
     int halo_rmax, halo_cmax;// last real row / column inside that block (edges replicate)
 };
 
-__device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
+// position of a strip: image, block row, strip inside the block row.  Found by division once per warp and
+// then advanced incrementally (a warp's strips are `nwarps` apart).
+struct StripPos {
+    uint32_t img, brow, sx;
+};
+
+__device__ __forceinline__ StripPos strip_pos(const Geom &g, uint32_t s)
 {
     const uint32_t per_image = (uint32_t)g.bh * (uint32_t)g.spr;
-    const uint32_t img = s / per_image;
-    const uint32_t rem = s - img * per_image;
-    const uint32_t brow = rem / (uint32_t)g.spr;
-    const uint32_t sx = rem - brow * (uint32_t)g.spr;
+    StripPos p;
+    p.img = s / per_image;
+    const uint32_t rem = s - p.img * per_image;
+    p.brow = rem / (uint32_t)g.spr;
+    p.sx = rem - p.brow * (uint32_t)g.spr;
+    return p;
+}
+
+__device__ __forceinline__ void strip_advance(const Geom &g, StripPos &p, uint32_t dq, uint32_t dr)
+{
+    p.sx += dr;
+    p.brow += dq;
+    if (p.sx >= (uint32_t)g.spr) {
+        p.sx -= (uint32_t)g.spr;
+        ++p.brow;
+    }
+    while (p.brow >= (uint32_t)g.bh) {
+        p.brow -= (uint32_t)g.bh;
+        ++p.img;
+    }
+}
+
+__device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
+{
+    const uint32_t img = p.img, brow = p.brow, sx = p.sx;
     StripCtx c;
     c.pitch = g.row_pitch;
     c.row0 = g.rgb + (uint64_t)img * g.image_stride + (int64_t)(brow * 8u) * c.pitch + (uint64_t)sx * 768u;
@@ -76,10 +103,7 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
     c.rmax = min(7, g.h - 1 - (int)(brow * 8u));                          // converter.c:31
     c.npx = min(256, g.w - (int)(sx * 256u));
     c.vb = min(32, g.bw - (int)(sx * 32u));
-    const uint32_t m0 = (uint32_t)((uintptr_t)c.row0 & 15u), step = (uint32_t)c.pitch & 15u;
-    c.mispack = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) c.mispack |= ((m0 + (uint32_t)min(r, c.rmax) * step) & 15u) << (4 * r);
+    c.mispack = 0;                                  // filled in by strip_issue_loads
     if (sx > 0) {                                   // previous block is in the same block row
         c.halo = c.row0 - 24;
         c.halo_rmax = c.rmax;
@@ -96,24 +120,22 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, uint32_t s)
     return c;
 }
 
-// stage the strip's 8 pixel rows: one TMA bulk copy per row (cp.async.bulk -> UBLKCP), issued by one
-// lane and completed through the warp's mbarrier.  Each copy starts at the row's 16-byte-aligned
-// address and covers whole 16-byte chunks, so any width / base alignment works.
-__device__ __forceinline__ void strip_issue_loads(const StripCtx &c, uint8_t *raw, uint64_t *bar, int lane)
+// stage the strip's 8 pixel rows: one TMA bulk copy per row (cp.async.bulk -> UBLKCP), lane r issuing
+// row r, all completed through the warp's mbarrier.  Each copy starts at the row's 16-byte-aligned
+// address and covers whole 16-byte chunks, so any width / base alignment works.  Also records the
+// rows' 16-byte phases in c.mispack.  Must be called by the whole warp.
+__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane)
 {
-    if (lane == 0) {
-        fence_proxy_async();                             // the tile was just read through the generic proxy
-        uint32_t total = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) total += (((c.mispack >> (4 * r)) & 15u) + 3u * (uint32_t)c.npx + 15u) & ~15u;
-        mbar_expect_tx(bar, total);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint32_t mis = (c.mispack >> (4 * r)) & 15u;
-            const uint8_t *a0 = c.row0 + (int64_t)min(r, c.rmax) * c.pitch - mis;
-            bulk_g2s(raw + r * RAW_PITCH, a0, (mis + 3u * (uint32_t)c.npx + 15u) & ~15u, bar);   // <= 784 bytes
-        }
-    }
+    const int r = lane & 7;
+    const uint8_t *row = c.row0 + (int64_t)min(r, c.rmax) * c.pitch;
+    const uint32_t mis = (uint32_t)(uintptr_t)row & 15u;
+    const uint32_t bytes = lane < 8 ? (mis + 3u * (uint32_t)c.npx + 15u) & ~15u : 0u;     // <= 784
+    c.mispack = __reduce_or_sync(0xffffffffu, lane < 8 ? mis << (4 * r) : 0u);
+    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+    fence_proxy_async();                                 // the tile was just read through the generic proxy
+    if (lane == 0) mbar_expect_tx(bar, total);
+    __syncwarp();
+    if (lane < 8) bulk_g2s(raw + r * RAW_PITCH, row - mis, bytes, bar);
 }
 
 // luma of 4 consecutive pixels held in 3 words: Y = (77R + 150G + 29B) >> 8  (converter.c:51)
@@ -183,10 +205,16 @@ __host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 
 
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
 k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blkinfo,
-               StripRec *__restrict__ strips, const uint8_t *__restrict__ tables,
+               StripRec *__restrict__ strips, uint32_t *__restrict__ strip_bits, const uint8_t *__restrict__ tables,
                unsigned long long *__restrict__ flagged_counter, const int exact_mode,
-               uint64_t *__restrict__ lookback_state, const uint64_t lookback_words)
+               uint64_t *__restrict__ lookback_state, const uint64_t lookback_words,
+               unsigned long long *__restrict__ trace)
 {
+#ifdef JPEGB200_TRACE   // tracing build only (make trace -> libjpegb200_trace.so)
+#define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * K1_WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define K1_TRACE(slot) do { } while (0)
+#endif
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *aclut = smem;
     const uint8_t *s_dclen = smem + TBL_DC_LEN;
@@ -194,9 +222,15 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     uint8_t *raw = smem + ACLUT_BYTES + warp * K1_WARP_SMEM;
     uint8_t *ybuf = raw + RAW_BYTES;
 
+    K1_TRACE(0);
+    // Static schedule: persistent warp i takes strips i, i + nwarps, ...; the 8 warps of a CTA work on 8
+    // consecutive strips (contiguous 6 KB runs of the same pixel rows).  Measured alternatives: interleaving
+    // warp indices across CTAs balances a partial last round over the SMs but loses that locality (+4 %
+    // time); handing strips out by ticket cannot balance a ~2-round image either, because the next strip
+    // must be known a whole strip ahead for the prefetch.
     const uint32_t nwarps = gridDim.x * K1_WARPS;
-    uint32_t s = blockIdx.x * K1_WARPS + warp;
     const uint32_t total = (uint32_t)g.total_strips;
+    uint32_t s = blockIdx.x * K1_WARPS + warp;
     __shared__ __align__(8) uint64_t s_bar[K1_WARPS + 1];      // one mbarrier per warp (pixel tiles) + one for the table
     uint64_t *bar = &s_bar[warp];
     if (lane == 0) mbar_init(bar, 1);
@@ -205,8 +239,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     __syncthreads();
     uint32_t phase = 0;
     StripCtx cur;
+    StripPos pos;
+    const uint32_t dq = nwarps / (uint32_t)g.spr, dr = nwarps - dq * (uint32_t)g.spr;
     if (s < total) {
-        cur = strip_ctx(g, s);
+        pos = strip_pos(g, s);
+        cur = strip_ctx(g, pos);
         strip_issue_loads(cur, raw, bar, lane);                  // first strip's pixels are in flight ...
     }
     if (threadIdx.x == 0) {                                      // ... while the bit-cost table is staged (one 16 KB bulk copy)
@@ -218,7 +255,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;
          i += (uint64_t)gridDim.x * K1_THREADS)
         lookback_state[i] = 0;
-    mbar_wait(&s_bar[K1_WARPS], 0);
+    bool table_ready = false;                                    // waited for at its first use
+    K1_TRACE(1);
 
     uint32_t nflag = 0;
     const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
@@ -237,6 +275,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
+        if (!table_ready) K1_TRACE(2);
 
         // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
         if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
@@ -269,7 +308,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         // raw tile is free: prefetch the next strip while this one is transformed
         const StripCtx me = cur;
         if (s + nwarps < total) {
-            cur = strip_ctx(g, s + nwarps);
+            strip_advance(g, pos, dq, dr);
+            cur = strip_ctx(g, pos);
             strip_issue_loads(cur, raw, bar, lane);
         }
 
@@ -387,6 +427,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 }
             }
 
+            if (!table_ready) {
+                K1_TRACE(3);
+                mbar_wait(&s_bar[K1_WARPS], 0);                    // the bit-cost table, staged during the first transform
+                K1_TRACE(4);
+            }
             // AC bit cost: code length + amplitude bits per non-zero coefficient, ZRLs, EOB
             uint32_t bits = 0, lastk = 0;                          // lastk = ACLUT_STRIDE * (index of the last non-zero)
 #pragma unroll
@@ -405,6 +450,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             dst[1] = make_uint4(zw[4], zw[5], zw[6], zw[7]);
             dst[2] = make_uint4(zw[8], zw[9], zw[10], zw[11]);
             dst[3] = make_uint4(zw[12], zw[13], zw[14], zw[15]);
+        }
+        if (!table_ready) {
+            mbar_wait(&s_bar[K1_WARPS], 0);                        // lanes without a block; immediate for the others
+            table_ready = true;
+            K1_TRACE(5);
         }
         // DC-difference costs (rle.c:68-76).  The strip's first block is predicted from the block
         // before the strip, whose quantized DC follows from its 64 luma values alone (an exact integer
@@ -427,11 +477,16 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             }
             const int first_dc = __shfl_sync(0xffffffffu, my_dc, 0);
             if (lane < me.vb) blkinfo[me.block0 + (uint32_t)lane] = blk_pack(incl - my_bits, my_last);
-            if (lane == me.vb - 1) strips[s] = StripRec{incl, (int16_t)first_dc, (int16_t)my_dc};
+            if (lane == me.vb - 1) {
+                strips[s] = StripRec{incl, (int16_t)first_dc, (int16_t)my_dc};
+                strip_bits[s] = incl;
+            }
         }
         __syncwarp();
     }
 
+    K1_TRACE(6);
+#undef K1_TRACE
     if (flagged_counter) {
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 8);

@@ -123,11 +123,12 @@ static void build_tables(HostTables &t)
                 if (sz > 7) continue;
                 const HuffCode hc = ac[(run << 4) | sz];
                 const uint32_t amp = (uint32_t)(v > 0 ? v : v - 1) & ((1u << sz) - 1u);
-                sym[run * 256 + b] = ((((uint32_t)hc.code << sz) | amp) << 5) | (uint32_t)(hc.len + sz);
+                const uint32_t len = (uint32_t)(hc.len + sz);                          // <= 16 + 7
+                sym[run * 256 + b] = ((((uint32_t)hc.code << sz) | amp) << (32u - len)) | len;
             }
         }
-        sym[0] = ((uint32_t)ac[0x00].code << 5) | ac[0x00].len;            // EOB
-        sym[0x80] = ((uint32_t)ac[0xF0].code << 5) | ac[0xF0].len;         // ZRL
+        sym[0] = ((uint32_t)ac[0x00].code << (32 - ac[0x00].len)) | ac[0x00].len;      // EOB
+        sym[0x80] = ((uint32_t)ac[0xF0].code << (32 - ac[0xF0].len)) | ac[0xF0].len;   // ZRL
     }
     memcpy(&t.block[TBL_AC_CODE], t.ac_code, sizeof(t.ac_code));
     memcpy(&t.block[TBL_DC_CODE], t.dc_code, sizeof(t.dc_code));
@@ -166,7 +167,7 @@ struct jpegb200_encoder {
     int dct_mode = 0;
     int bytes_per_block = 24;
     jb::HostTables tables;
-    jb::DeviceBuffer coef, blkinfo, strips, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace;
+    jb::DeviceBuffer coef, blkinfo, strips, strip_bits, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace, trace1;
     // last launch
     jb::PackArgs args{};
     jb::Geom geom{};
@@ -271,6 +272,7 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     if ((rc = enc->coef.reserve(tb * 64))) return rc;
     if ((rc = enc->blkinfo.reserve(tb * 4))) return rc;
     if ((rc = enc->strips.reserve(g.total_strips * sizeof(StripRec)))) return rc;
+    if ((rc = enc->strip_bits.reserve(g.total_strips * 4 + 16))) return rc;
     // grouped look-back state of K2 (aggregate per tile + inclusive prefix per 1024-tile group), once
     // for the bit offsets and once for the stuffed-zero counts; contiguous, cleared by K1's prologue
     const int groups = (tiles + LB_GROUP - 1) / LB_GROUP;
@@ -289,6 +291,7 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.coef = static_cast<const int8_t *>(enc->coef.ptr);
     a.blkinfo = static_cast<const uint32_t *>(enc->blkinfo.ptr);
     a.strips = static_cast<const StripRec *>(enc->strips.ptr);
+    a.strip_bits = static_cast<const uint32_t *>(enc->strip_bits.ptr);
     a.bit_incl = static_cast<uint64_t *>(enc->lookback.ptr);
     a.ff_agg = a.bit_incl + (uint64_t)groups * (uint64_t)count;
     a.ff_incl = a.ff_agg + (uint64_t)tiles * (uint64_t)count;
@@ -345,14 +348,19 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     const Geom &g = enc->geom;
     const uint64_t want = (g.total_strips + K1_WARPS - 1) / K1_WARPS;
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
+    if (getenv("JPEGB200_K1_TRACE")) {              // tuning aid: per-warp timestamps
+        if (int rc = enc->trace1.reserve((uint64_t)grid * K1_WARPS * 64)) return rc;
+        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * K1_WARPS * 64, st));
+    }
     {
         TimedLaunch t(enc, st, KID_BLOCK);
         k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
                                                            static_cast<uint32_t *>(enc->blkinfo.ptr),
                                                            static_cast<StripRec *>(enc->strips.ptr),
+                                                           static_cast<uint32_t *>(enc->strip_bits.ptr),
                                                            static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc),
                                                            enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
-                                                           enc->lookback_words);
+                                                           enc->lookback_words, static_cast<unsigned long long *>(enc->trace1.ptr));
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -374,7 +382,8 @@ static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
         per_sm = n > 0 ? n : 1;
     }
     const uint64_t total = (uint64_t)a.tiles * (uint64_t)a.count;
-    const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);
+    unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);
+    if (const char *e = getenv("JPEGB200_K2_GRID")) grid = std::max(1u, std::min(grid, (unsigned)atoi(e)));   // tuning aid
     enc->args.dynamic_tiles = total > grid ? 1 : 0;            // more tiles than one wave: persistent CTAs + ticket counter
     {
         TimedLaunch t(enc, st, KID_ENTROPY);
@@ -476,8 +485,8 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
     cudaSetDevice(enc->device);
     cudaDeviceSynchronize();
     harvest_events(enc);
-    for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->strips, &enc->lookback, &enc->image_bits, &enc->image_bytes,
-                            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace})
+    for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
+                            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace, &enc->trace1})
         b->release();
     delete enc;
 }
@@ -581,6 +590,15 @@ extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t
 // per-block bit cost, reconstructed from K1's strip-local offsets and strip records exactly the
 // way K2 consumes them
 // tuning aid (JPEGB200_K2_TRACE=1): per-tile phase timestamps of the last K2 launch, [tiles][8] ns
+extern "C" int jpegb200_encoder_read_k1_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t nwarps)
+{
+    if (!enc || !host || !enc->trace1.ptr || nwarps * 64 > enc->trace1.bytes) return JPEGB200_ERR_ARG;
+    JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    JB_CUDA(cudaMemcpy(host, enc->trace1.ptr, nwarps * 64, cudaMemcpyDeviceToHost));
+    return JPEGB200_OK;
+}
+
 extern "C" int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t ntiles)
 {
     if (!enc || !host || !enc->trace.ptr || ntiles * 64 > enc->trace.bytes) return JPEGB200_ERR_ARG;

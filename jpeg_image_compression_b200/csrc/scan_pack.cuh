@@ -31,7 +31,7 @@ namespace jb {
 constexpr int K2_WARPS = 8;                                    // strips per tile
 constexpr int K2_THREADS = K2_WARPS * 32;
 constexpr int K2_MAX_BLOCK_BITS = 1472;                       // >= 14 + 63*23 = 1463: any tile fits
-constexpr int K2_SMALL_BLOCK_BITS = 512;                      // default window: 64 bytes per block on average
+constexpr int K2_SMALL_BLOCK_BITS = 256;                      // default window: 32 bytes per block (4 bits per pixel) on average
 constexpr int k2_win_words(int block_bits) { return (K2_THREADS * block_bits) / 32 + 8; }
 
 // one record per strip, written by K1
@@ -57,13 +57,14 @@ constexpr int TBL_BYTES = TBL_SYM + 16384 + 32;
 
 constexpr int K2_STAGE_STRIDE = 17;                            // words per lane in the coefficient staging area
 constexpr int K2_SYM_WORDS = 16 * 256;                         // AC symbol table staged in shared memory
-constexpr int k2_smem(int block_bits) { return (k2_win_words(block_bits) + K2_THREADS * K2_STAGE_STRIDE + K2_SYM_WORDS) * 4; }
+constexpr int k2_smem(int block_bits) { return (2 * k2_win_words(block_bits) + K2_THREADS * K2_STAGE_STRIDE + K2_SYM_WORDS) * 4; }
 
 struct PackArgs {
     const uint8_t *tables;         // device table block (TBL_* offsets)
     const int8_t *coef;            // [count*nb_avail][64] zig-zag int8
     const uint32_t *blkinfo;       // [count*nb_avail]
     const StripRec *strips;        // [count*strips_avail]
+    const uint32_t *strip_bits;    // [count*strips_avail] compact copy of StripRec.bits (read four at a time)
     uint64_t *bit_incl;            // bit-offset checkpoints, one per 1024-tile group: [count*groups]
     uint64_t *ff_agg, *ff_incl;    // grouped look-back state of the stuffed-zero counts: [count*tiles], [count*groups]
     unsigned long long *tile_counter;   // next tile to hand out (cleared together with the look-back state)
@@ -98,53 +99,62 @@ __device__ __forceinline__ uint32_t strip_blocks(uint32_t strip_in_image, uint32
     return min(32u, bw - sx * 32u);
 }
 
-// MSB-first bit appender with a 32-bit register accumulator.  The window word that holds the
-// block's first bit and the one that holds its last bit may be shared with the neighbouring
-// blocks (atomicOr); words in between belong to this block alone (plain store).
+// shared-memory accesses by 32-bit shared-space address: keeps the symbol loop free of the
+// generic-to-shared address arithmetic the compiler otherwise repeats at every access
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v, bool enable)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p red.shared.or.b32 [%0], %1;\n}"
+                 :: "r"(saddr), "r"(v), "r"((uint32_t)enable) : "memory");
+}
+
+// MSB-first bit appender with a 32-bit register accumulator, flushed word-wise into the zeroed
+// shared-memory window with OR-reductions (the first and last word of a block are shared with its
+// neighbours).  Branch-free: the flush is predicated.
 struct BitWriter {
-    uint32_t *win;
-    uint32_t acc, wi, fill;
-    bool first;
-    __device__ __forceinline__ void start(uint32_t *w, uint32_t relbit)
+    uint32_t waddr;       // shared-space address of the window word being filled
+    uint32_t acc, fill;
+    __device__ __forceinline__ void start(uint32_t win_saddr, uint32_t relbit)
     {
-        win = w;
-        wi = relbit >> 5;
+        waddr = win_saddr + ((relbit >> 5) << 2);
         fill = relbit & 31u;
         acc = 0;
-        first = true;
     }
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n)            // n in 1..27, v < 2^n
+    __device__ __forceinline__ void put(uint32_t vl, uint32_t n)           // n in 1..27 bits, left-aligned in vl
     {
-        const uint32_t vl = v << (32u - n);                                // left-aligned
         acc |= vl >> fill;
         fill += n;
-        if (fill >= 32u) {
-            if (first) { atomicOr(win + wi, acc); first = false; }
-            else win[wi] = acc;
-            fill -= 32u;
-            acc = fill ? vl << (n - fill) : 0u;                            // the bits that did not fit
-            ++wi;
-        }
+        const bool full = fill >= 32u;
+        red_or_shared(waddr, acc, full);
+        fill &= 31u;
+        waddr += full ? 4u : 0u;
+        acc = full ? vl << (n - fill) : acc;                               // the bits that did not fit (none if fill == 0)
     }
-    __device__ __forceinline__ void finish()
-    {
-        if (fill) atomicOr(win + wi, acc);
-    }
+    __device__ __forceinline__ void finish() { red_or_shared(waddr, acc, fill != 0u); }
 };
 
-// append with clipping at bit `limit` (window-relative); used only for the halo blocks
-__device__ __forceinline__ void put_clipped(uint32_t *win, uint32_t &pos, uint32_t limit, uint32_t v, uint32_t n)
+// append n left-aligned bits with clipping at bit `limit` (window-relative); used only for the halo blocks
+__device__ __forceinline__ void put_clipped(uint32_t win_saddr, uint32_t &pos, uint32_t limit, uint32_t vl, uint32_t n)
 {
     if (pos >= limit) return;
-    if (pos + n > limit) {
-        const uint32_t keep = limit - pos;
-        v >>= (n - keep);
-        n = keep;
-    }
-    const uint64_t x = ((uint64_t)v << (64u - n)) >> (pos & 31u);
+    if (pos + n > limit) n = limit - pos;
+    vl &= 0xFFFFFFFFu << (32u - n);                              // n >= 1
+    const uint64_t x = ((uint64_t)vl << 32) >> (pos & 31u);
     const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
-    if (hi) atomicOr(win + (pos >> 5), hi);
-    if (lo) atomicOr(win + (pos >> 5) + 1, lo);
+    const uint32_t wa = win_saddr + ((pos >> 5) << 2);
+    red_or_shared(wa, hi, hi != 0u);
+    red_or_shared(wa + 4u, lo, lo != 0u);
     pos += n;
 }
 
@@ -156,34 +166,28 @@ __device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
 }
 
 // Walk one block's symbols (rle.c:59-124) and hand (value, nbits) pairs (huffman.c:145-173) to
-// emit(), which returns false to stop early.  sw: the block's 16 coefficient words in shared
-// memory (zig-zag order, int8).
+// emit(), which returns false to stop early.  sw: shared-space address of the block's 16 coefficient
+// words (zig-zag order, int8); sym, dc: shared-space addresses of the symbol tables.
 // The lane first builds the 63-bit map of its non-zero AC coefficients and then visits only
 // those: the loop trip count is the lane's symbol count, so a warp runs max-over-lanes symbols
 // instead of one divergent branch per coefficient position.  Each visit is one table look-up:
-// s_sym[run & 15][value & 255] = (Huffman code << size | amplitude bits) << 5 | total length,
-// i.e. huffman.c:164-173 applied to the symbol rle.c:106-113 would have produced.
+// sym[run & 15][value & 255] = (Huffman code << size | amplitude bits), left-aligned in the word, with
+// the total length in the low 5 bits, i.e. huffman.c:164-173 applied to the symbol rle.c:106-113 would
+// have produced.  emit() receives (left-aligned bits, count).
+// mlo/mhi: the block's non-zero map (bit k <-> zig-zag position k, DC excluded), built by the caller
+// from the coefficient words while they were in registers.
 template <typename Emit>
-__device__ __forceinline__ void encode_block(const uint32_t *sw, int prev_dc, int last, const uint32_t *s_sym,
-                                             const uint32_t *s_dc, Emit emit)
+__device__ __forceinline__ void encode_block(uint32_t sw, int my_dc, int prev_dc, int last, uint32_t mlo, uint32_t mhi,
+                                             uint32_t sym, uint32_t dc, Emit emit)
 {
-    const uint32_t w0 = sw[0];
     {
-        const int diff = (int)(int8_t)(w0 & 0xFFu) - prev_dc;                          // rle.c:68-70
+        const int diff = my_dc - prev_dc;                                              // rle.c:68-70
         const int sz = magnitude_class(diff);
-        const uint32_t hc = s_dc[sz];
+        const uint32_t hc = lds_u32(dc + 4u * (uint32_t)sz);
         const uint32_t amp = (uint32_t)(diff > 0 ? diff : diff - 1) & ((1u << sz) - 1u);   // rle.c:24-35, huffman.c:39
-        if (!emit(((hc >> 8) << sz) | amp, (hc & 0xFFu) + sz)) return;
+        const uint32_t n = (hc & 0xFFu) + (uint32_t)sz;
+        if (!emit((((hc >> 8) << sz) | amp) << (32u - n), n)) return;
     }
-    uint32_t mlo = nonzero_nibble(w0 & 0xFFFFFF00u), mhi = 0;     // bit k <-> zig-zag position k
-    const int lastw = last >> 2;
-#pragma unroll
-    for (int w = 1; w < 8; ++w)
-        if (w <= lastw) mlo |= nonzero_nibble(sw[w]) << (4 * w);
-#pragma unroll
-    for (int w = 8; w < 16; ++w)
-        if (w <= lastw) mhi |= nonzero_nibble(sw[w]) << (4 * (w - 8));
-    const uint8_t *sb = reinterpret_cast<const uint8_t *>(sw);
     int prev = 0;                                                 // position of the previous non-zero (0 = DC)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -192,23 +196,23 @@ __device__ __forceinline__ void encode_block(const uint32_t *sw, int prev_dc, in
         while (m) {
             const int k = 32 * half + __ffs((int)m) - 1;
             m &= m - 1;
-            const uint32_t byte = sb[k];
+            const uint32_t byte = lds_u8(sw + (uint32_t)k);
             int run = k - prev - 1;
             prev = k;
             if (run >= 16) {                                                           // ZRL, rle.c:99-103
-                const uint32_t z = s_sym[0x80];           // slot (run 0, value -128: cannot occur) holds the ZRL code
+                const uint32_t z = lds_u32(sym + 4u * 0x80u);   // slot (run 0, value -128: cannot occur) holds the ZRL code
                 do {
-                    if (!emit(z >> 5, z & 31u)) return;
+                    if (!emit(z & ~31u, z & 31u)) return;
                     run -= 16;
                 } while (run >= 16);
             }
-            const uint32_t e = s_sym[(run << 8) | byte];
-            if (!emit(e >> 5, e & 31u)) return;
+            const uint32_t e = lds_u32(sym + 4u * (((uint32_t)run << 8) | byte));
+            if (!emit(e & ~31u, e & 31u)) return;
         }
     }
     if (last < 63) {                                                                   // EOB, rle.c:121-123
-        const uint32_t e = s_sym[0];                      // slot (run 0, value 0) holds the EOB code
-        emit(e >> 5, e & 31u);
+        const uint32_t e = lds_u32(sym);                      // slot (run 0, value 0) holds the EOB code
+        emit(e & ~31u, e & 31u);
     }
 }
 
@@ -220,255 +224,339 @@ __device__ __forceinline__ uint32_t count_ff_bytes(uint32_t w)
     return __popc(x & 0x01010101u);
 }
 
-// BLOCK_BITS: window capacity per block.  The default instantiation (512) keeps shared memory small
-// (12 CTAs per SM); a tile that does not fit raises ERRBIT_WORKSPACE and the caller re-runs with the
-// worst-case instantiation (1472), selected through jpegb200_encoder_set_bytes_per_block.
-__device__ __forceinline__ unsigned long long globaltimer_ns()
+// window word i restricted to the owned window bytes [wb0, wb1) (bytes are MSB first inside a word)
+__device__ __forceinline__ uint32_t masked_word(const uint32_t *win, uint32_t i, uint32_t wb0, uint32_t wb1)
 {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+    uint32_t v = win[i];
+    const uint32_t lo = i * 4, hi = lo + 4;
+    if (lo < wb0) v &= 0xFFFFFFFFu >> (8 * (wb0 - lo));
+    if (hi > wb1) v &= wb1 > lo ? 0xFFFFFFFFu << (8 * (hi - wb1)) : 0u;
+    return v;
 }
-#define K2_TRACE(slot) do { if (a.trace && tid == 0) a.trace[t * 8 + (slot)] = globaltimer_ns(); } while (0)
+
+// BLOCK_BITS: window capacity per block.  The default instantiation (256: four bits per pixel on
+// average over a tile) keeps shared memory small (4 CTAs per SM); a tile that does not fit raises
+// ERRBIT_WORKSPACE and the caller re-runs with the worst-case instantiation (1472), selected through
+// jpegb200_encoder_set_bytes_per_block.
+// phase timestamps exist only in the tracing build of the library (make trace -> libjpegb200_trace.so)
+#ifdef JPEGB200_TRACE
+#define K2_TRACE(tile_id, slot) do { if (a.trace && tid == 0) a.trace[(tile_id) * 8 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define K2_TRACE(tile_id, slot) do { } while (0)
+#endif
+
+// A packed tile whose bytes are not written yet.  A CTA packs tile i+1 before it resolves the
+// stuffed-zero look-back of tile i and writes it out: by then every predecessor has published its
+// count, so the look-back never waits in steady state (two bit windows, used alternately).
+struct PendingTile {
+    uint64_t t;          // ticket (img * tiles + tile); ~0 = none
+    uint64_t w0;         // stream word index of window word 0
+    uint64_t B0, B1;     // owned stream bytes [B0, B1)
+    uint32_t tile_ff;    // 0xFF bytes among them
+};
 
 template <int BLOCK_BITS>
 __global__ void __launch_bounds__(K2_THREADS)
 k_scan_pack_stuff(const PackArgs a)
 {
     constexpr int WIN_WORDS = k2_win_words(BLOCK_BITS);
-    extern __shared__ __align__(16) uint32_t win[];          // [WIN_WORDS] bit window, then the staging area
-    uint32_t *stage = win + WIN_WORDS + (threadIdx.x * K2_STAGE_STRIDE);   // this lane's 16 coefficient words
+    extern __shared__ __align__(16) uint32_t k2_smem_words[];   // two bit windows, the staging area, the symbol table
+    uint32_t *stage = k2_smem_words + 2 * WIN_WORDS + (threadIdx.x * K2_STAGE_STRIDE);   // this lane's 16 coefficient words
+    uint32_t *s_sym = k2_smem_words + 2 * WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE;
     __shared__ uint32_t s_dc[16];
     __shared__ uint32_t s_strip_base[K2_WARPS];     // bit offset of each strip inside the tile
     __shared__ uint32_t s_warp[K2_WARPS], s_carry, s_tile_bits;
     __shared__ uint64_t s_scratch[9];
+    __shared__ __align__(8) uint64_t s_bar;         // completion of the symbol table's bulk copy
+    __shared__ unsigned long long s_next_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ unsigned long long s_next_tile;
-    if (tid == 0) s_next_tile = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : (unsigned long long)blockIdx.x;
-    uint32_t *s_sym = win + WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE;
-    for (int i = tid; i < K2_SYM_WORDS / 4; i += K2_THREADS)
-        reinterpret_cast<uint4 *>(s_sym)[i] = reinterpret_cast<const uint4 *>(a.tables + TBL_SYM)[i];
+    uint32_t smem_sa = smem_u32(k2_smem_words);                         // shared-space addresses for the symbol loop
+    asm volatile("mov.b32 %0, %0;" : "+r"(smem_sa));                    // opaque: computed once, not rematerialised at every use
+    const uint32_t stage_sa = smem_sa + (uint32_t)(2 * WIN_WORDS + tid * K2_STAGE_STRIDE) * 4u;
+    const uint32_t sym_sa = smem_sa + (uint32_t)(2 * WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE) * 4u;
+    const uint32_t dc_sa = smem_u32(s_dc);
+    if (tid == 0) {
+        s_next_tile = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : (unsigned long long)blockIdx.x;
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, K2_SYM_WORDS * 4);                 // 16 KB, one TMA bulk copy; awaited before the first pack
+        bulk_g2s(s_sym, a.tables + TBL_SYM, K2_SYM_WORDS * 4, &s_bar);
+    }
     if (tid < 16) s_dc[tid] = reinterpret_cast<const uint32_t *>(a.tables + TBL_DC_CODE)[tid];
+    bool sym_ready = false;
     const uint64_t origin = ((uint64_t)a.bit_phase + 7) >> 3;     // first stream byte this image/stripe owns
     const int groups = (a.tiles + LB_GROUP - 1) / LB_GROUP;
+    const uint64_t total_tiles = (uint64_t)a.tiles * (uint64_t)a.count;
 
     // Tiles wait on their predecessors (look-backs), so a tile must never be owned by a CTA that is not
     // running yet.  If all tiles fit in one wave the launch has one CTA per tile (tile = blockIdx.x: CTAs
     // are dispatched in index order).  Otherwise persistent CTAs draw tiles from an atomic counter,
     // strictly in increasing order and only once the CTA runs: every predecessor of a tile is then finished
-    // or in the hands of a running CTA that never waits on a later tile -- no deadlock even when only part
-    // of the grid is resident (e.g. next to another stream's kernels).
+    // or in the hands of a running CTA that publishes its counts without waiting on a later tile -- no
+    // deadlock even when only part of the grid is resident (e.g. next to another stream's kernels).
+    PendingTile pend;
+    pend.t = ~0ull;
+    int cur = 0;
     for (;;) {
         __syncthreads();
         const uint64_t t = s_next_tile;
-        if (t >= (uint64_t)a.tiles * (uint64_t)a.count) break;
-        const int img = (int)(t / (uint64_t)a.tiles), tile = (int)(t - (uint64_t)img * a.tiles);
-        const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
-        const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
-        const uint32_t nstrips = min((uint32_t)K2_WARPS, a.strips_owned - strip0);
-        const bool last_tile = tile == a.tiles - 1;
-        uint64_t *bit_incl = a.bit_incl + (uint64_t)img * groups;
-        uint64_t *ff_agg = a.ff_agg + (uint64_t)img * a.tiles, *ff_incl = a.ff_incl + (uint64_t)img * groups;
-
-        K2_TRACE(0);
-        // ---- 0. fetch this lane's block before any waiting (loads do not depend on the offsets) ----
-        const uint64_t img_block0 = (uint64_t)img * a.nb_avail;
-        const uint32_t my_strip = strip0 + warp;
-        const bool have = (uint32_t)warp < nstrips && (uint32_t)lane < strip_blocks(my_strip, a.spr, a.bw);
-        uint32_t info = 0;
-        int my_dc = 0;
-        if (have) {
-            const uint32_t brow = my_strip / a.spr, sx = my_strip - brow * a.spr;
-            const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lane;
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + b * 64);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint4 q = src[i];
-                stage[4 * i] = q.x; stage[4 * i + 1] = q.y; stage[4 * i + 2] = q.z; stage[4 * i + 3] = q.w;
-                if (i == 0) my_dc = (int)(int8_t)(q.x & 0xFFu);
-            }
-            info = a.blkinfo[b];
-        }
-        // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
-        // previous strip's last block for lane 0
-        int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
-        if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
-
-        K2_TRACE(1);
-        // ---- 1. tile bit offset: wait-free ---------------------------------------------------------
-        // K1 left complete per-strip bit counts (only the image's very first DC symbol is missing: its
-        // predictor is a run-time argument), so the offset is a plain sum over the earlier strips of the
-        // tile's 1024-tile group plus the group's checkpoint.
-        const uint32_t fix0 = c_dc_len[magnitude_class((int)recs[0].first_dc - (int)a.dc_pred0)];
-        const int g0 = (tile / LB_GROUP) * LB_GROUP;
-        uint64_t part = 0;
-        for (uint32_t sidx = (uint32_t)g0 * K2_WARPS + tid; sidx < strip0; sidx += K2_THREADS) part += recs[sidx].bits;
-        if (tid == 0) part += g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) s_scratch[warp] = part;
-        if (warp == 0) {
-            uint32_t tot = (uint32_t)lane < nstrips ? recs[strip0 + lane].bits : 0u;
-            if (tile == 0 && lane == 0) tot += fix0;
-            uint32_t incl = tot;
-#pragma unroll
-            for (int o = 1; o < K2_WARPS; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            if (lane == K2_WARPS - 1) s_tile_bits = incl;
-            if (lane < K2_WARPS) s_strip_base[lane] = incl - tot;
-        }
-        __syncthreads();
-        uint64_t bit_excl = 0;
-#pragma unroll
-        for (int w = 0; w < K2_WARPS; ++w) bit_excl += s_scratch[w];
-        const uint64_t begin = bit_excl + a.bit_phase, end = begin + s_tile_bits;
-        if (tid == 0) {
-            if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(bit_incl + tile / LB_GROUP, LB_VALID | (bit_excl + s_tile_bits));
-            if (last_tile) a.image_bits[img] = bit_excl + s_tile_bits;
-        }
-        K2_TRACE(2);
-        const uint64_t w0 = begin >> 5;
-        uint32_t nwords = (uint32_t)(((end + 31) >> 5) - w0);
-        const bool fits = nwords + 2 <= (uint32_t)WIN_WORDS;
-        if (!fits) {                                              // dense tile: needs the large-window instantiation
-            if (tid == 0) atomicOr(a.err, ERRBIT_WORKSPACE);
-            nwords = 0;
-        }
-        for (uint32_t i = tid; i < nwords + 2; i += K2_THREADS) win[i] = 0;
-        __syncthreads();
-
-        K2_TRACE(3);
-        // ---- 2. pack this tile's blocks ----------------------------------------------------------
-        if (have && fits) {
-            // K1's strip-local offsets are complete except in the image's first strip (fix0)
-            const uint64_t off = begin + s_strip_base[warp] + (info & 0xFFFFu) + (my_strip == 0 && lane ? fix0 : 0u);
-            BitWriter bw;
-            bw.start(win, (uint32_t)(off - (w0 << 5)));
-            encode_block(stage, prev_dc, (int)((info >> 16) & 63u), s_sym, s_dc,
-                         [&](uint32_t v, uint32_t n) { bw.put(v, n); return true; });
-            bw.finish();
-        }
-
-        // ---- 3. complete the last owned byte with the next tile's leading bits (at most 7) ---------
-        // Bytes are owned by the tile that holds their first bit.  Runs concurrently with the packing
-        // above: it only ORs into bits at or after `end`.
-        const uint64_t limit = (end + 7) & ~7ull;                // first bit NOT owned by this tile
-        if (tid == 0 && fits && (end & 7u) && !(last_tile && a.strips_avail == a.strips_owned)) {
-            uint32_t pos = (uint32_t)(end - (w0 << 5));
-            const uint32_t lim = (uint32_t)(limit - (w0 << 5));
-            uint32_t st = strip0 + nstrips;                      // raster successor of the tile's last block
-            int hprev = (int)recs[st - 1].last_dc;
-            uint32_t lb = 0;
-            for (int n = 0; n < 2 && pos < lim && st < a.strips_avail; ++n) {
-                const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
-                const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) stage[i] = src[i];
-                const uint32_t hinfo = a.blkinfo[b];
-                encode_block(stage, hprev, (int)((hinfo >> 16) & 63u), s_sym, s_dc, [&](uint32_t v, uint32_t nb) {
-                    put_clipped(win, pos, lim, v, nb);
-                    return pos < lim;
-                });
-                hprev = (int)(int8_t)(stage[0] & 0xFFu);
-                if (++lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
-            }
-        }
-        __syncthreads();
-
-        K2_TRACE(4);
-        // ---- 4. stuffing ---------------------------------------------------------------------------
-        // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
-        const uint64_t B0 = (begin + 7) >> 3, B1 = fits ? (end + 7) >> 3 : B0;
-        const uint32_t wb0 = (uint32_t)(B0 - 4 * w0), wb1 = (uint32_t)(B1 - 4 * w0);   // window byte range
-        const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;                      // window word range [wfirst, wlast)
-        auto masked_word = [&](uint32_t i) -> uint32_t {
-            uint32_t v = win[i];
-            const uint32_t lo = i * 4, hi = lo + 4;               // bytes lo..hi-1 (MSB first)
-            if (lo < wb0) v &= 0xFFFFFFFFu >> (8 * (wb0 - lo));
-            if (hi > wb1) v &= wb1 > lo ? 0xFFFFFFFFu << (8 * (hi - wb1)) : 0u;
-            return v;
-        };
-        uint32_t mine = 0;
-        for (uint32_t i = wfirst + tid; i < wlast; i += K2_THREADS) mine += count_ff_bytes(masked_word(i));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if (lane == 0) s_warp[warp] = mine;
-        __syncthreads();
-        uint32_t tile_ff = 0;
-#pragma unroll
-        for (int w = 0; w < K2_WARPS; ++w) tile_ff += s_warp[w];
-        K2_TRACE(5);
-        if (tid == 0) st_volatile_u64(ff_agg + tile, LB_VALID | tile_ff);
-        const uint64_t ff_excl = lookback_grouped(ff_agg, ff_incl, tile, a.err, s_scratch);
+        const bool have_tile = t < total_tiles;
+        PendingTile mine;
+        mine.t = ~0ull;
         unsigned long long ticket = ~0ull;
-        if (tid == 0) {
-            if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(ff_incl + tile / LB_GROUP, LB_VALID | (ff_excl + tile_ff));
-            s_carry = 0;
-            // next ticket, kept in a register until after the write-out so that its round trip overlaps
-            // it (static launches process exactly one tile)
-            ticket = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : ~0ull;
-            if (last_tile) {
-                const uint64_t size = B1 - origin + ff_excl + tile_ff;
-                a.image_bytes[img] = size;
-                if (a.count == 1) {
-                    a.scan_offsets[0] = 0;
-                    a.scan_offsets[1] = size;
+        if (have_tile) {
+            uint32_t *win = k2_smem_words + cur * WIN_WORDS;
+            const uint32_t win_sa = smem_sa + (uint32_t)(cur * WIN_WORDS) * 4u;
+            const int img = (int)(t / (uint64_t)a.tiles), tile = (int)(t - (uint64_t)img * a.tiles);
+            const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
+            const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
+            const uint32_t nstrips = min((uint32_t)K2_WARPS, a.strips_owned - strip0);
+            const bool last_tile = tile == a.tiles - 1;
+            uint64_t *bit_incl = a.bit_incl + (uint64_t)img * groups;
+
+            K2_TRACE(t, 0);
+            // ---- 0. fetch this lane's block before any waiting (loads do not depend on the offsets) ----
+            const uint64_t img_block0 = (uint64_t)img * a.nb_avail;
+            const uint32_t my_strip = strip0 + warp;
+            const bool have = (uint32_t)warp < nstrips && (uint32_t)lane < strip_blocks(my_strip, a.spr, a.bw);
+            uint32_t info = 0, mlo = 0, mhi = 0;                     // non-zero map of the block's AC coefficients
+            int my_dc = 0;
+            if (have) {
+                const uint32_t brow = my_strip / a.spr, sx = my_strip - brow * a.spr;
+                const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lane;
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + b * 64);
+                uint4 q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = src[i];
+                info = a.blkinfo[b];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    stage[4 * i] = q[i].x; stage[4 * i + 1] = q[i].y; stage[4 * i + 2] = q[i].z; stage[4 * i + 3] = q[i].w;
+                    const uint32_t m16 = nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) |
+                                         (nonzero_nibble(q[i].w) << 12);
+                    if (i < 2) mlo |= m16 << (16 * i);
+                    else mhi |= m16 << (16 * (i - 2));
                 }
-                if (size > a.out_capacity) atomicOr(a.err, a.count == 1 ? ERRBIT_OUTPUT : ERRBIT_WORKSPACE);
+                mlo &= ~1u;                                          // position 0 is the DC
+                my_dc = (int)(int8_t)(q[0].x & 0xFFu);
             }
-        }
-        __syncthreads();
-        K2_TRACE(6);
-        uint8_t *out = a.out + (uint64_t)img * a.out_slot;
-        const uint64_t out_base = (B0 - origin) + ff_excl;        // output index of window byte wb0
-        for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
-            const uint32_t i = i0 + tid;
-            const uint32_t v = i < wlast ? masked_word(i) : 0u;
-            const uint32_t cnt = count_ff_bytes(v);
-            uint32_t incl = cnt;
+            // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
+            // previous strip's last block for lane 0
+            int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+            if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
+
+            K2_TRACE(t, 1);
+            // ---- 1. tile bit offset: wait-free ---------------------------------------------------------
+            // K1 left complete per-strip bit counts (only the image's very first DC symbol is missing: its
+            // predictor is a run-time argument), so the offset is a plain sum over the earlier strips of the
+            // tile's 1024-tile group (read from the compact copy of the counts, four per load) plus the
+            // group's checkpoint.
+            const uint32_t fix0 = c_dc_len[magnitude_class((int)recs[0].first_dc - (int)a.dc_pred0)];
+            const int g0 = (tile / LB_GROUP) * LB_GROUP;
+            uint64_t part = 0;
+            {
+                const uint64_t base = (uint64_t)img * a.strips_avail;            // index of the image's strip 0
+                const uint32_t *sbits = a.strip_bits + base;
+                const uint32_t lo = (uint32_t)g0 * K2_WARPS, hi = strip0;
+                const uint32_t head = min(hi, lo + ((4u - (uint32_t)((base + lo) & 3u)) & 3u));   // up to 16-byte alignment
+                if (lo + tid < head) part += sbits[lo + tid];
+                const uint32_t nvec = (hi - head) >> 2, tail = head + 4u * nvec;
+                const uint4 *v4 = reinterpret_cast<const uint4 *>(sbits + head);
+                for (uint32_t i = tid; i < nvec; i += K2_THREADS) {
+                    const uint4 v = v4[i];
+                    part += (uint64_t)(v.x + v.y) + (uint64_t)(v.z + v.w);
+                }
+                if (tail + tid < hi) part += sbits[tail + tid];
+            }
+            if (tid == 0) part += g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) s_scratch[warp] = part;
+            if (warp == 0) {
+                uint32_t tot = (uint32_t)lane < nstrips ? recs[strip0 + lane].bits : 0u;
+                if (tile == 0 && lane == 0) tot += fix0;
+                uint32_t incl = tot;
+#pragma unroll
+                for (int o = 1; o < K2_WARPS; o <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                if (lane == K2_WARPS - 1) s_tile_bits = incl;
+                if (lane < K2_WARPS) s_strip_base[lane] = incl - tot;
             }
-            if (lane == 31) s_warp[warp] = incl;
             __syncthreads();
-            uint32_t before = s_carry + incl - cnt;
-            uint32_t round_total = 0;
+            uint64_t bit_excl = 0;
 #pragma unroll
-            for (int w = 0; w < K2_WARPS; ++w) {
-                const uint32_t ws = s_warp[w];
-                if (w < warp) before += ws;
-                round_total += ws;
+            for (int w = 0; w < K2_WARPS; ++w) bit_excl += s_scratch[w];
+            const uint64_t begin = bit_excl + a.bit_phase, end = begin + s_tile_bits;
+            if (tid == 0) {
+                if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(bit_incl + tile / LB_GROUP, LB_VALID | (bit_excl + s_tile_bits));
+                if (last_tile) a.image_bits[img] = bit_excl + s_tile_bits;
             }
-            if (i < wlast) {
-                const uint32_t raw = win[i];
-                uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
+            K2_TRACE(t, 2);
+            const uint64_t w0 = begin >> 5;
+            uint32_t nwords = (uint32_t)(((end + 31) >> 5) - w0);
+            const bool fits = nwords + 2 <= (uint32_t)WIN_WORDS;
+            if (!fits) {                                              // dense tile: needs the large-window instantiation
+                if (tid == 0) atomicOr(a.err, ERRBIT_WORKSPACE);
+                nwords = 0;
+            }
+            for (uint32_t i = tid; i < nwords + 2; i += K2_THREADS) win[i] = 0;
+            if (!sym_ready) {
+                mbar_wait(&s_bar, 0);
+                sym_ready = true;
+            }
+            __syncthreads();
+
+            K2_TRACE(t, 3);
+            // ---- 2. pack this tile's blocks ----------------------------------------------------------
+            if (have && fits) {
+                // K1's strip-local offsets are complete except in the image's first strip (fix0)
+                const uint64_t off = begin + s_strip_base[warp] + (info & 0xFFFFu) + (my_strip == 0 && lane ? fix0 : 0u);
+                BitWriter bw;
+                bw.start(win_sa, (uint32_t)(off - (w0 << 5)));
+                encode_block(stage_sa, my_dc, prev_dc, (int)((info >> 16) & 63u), mlo, mhi, sym_sa, dc_sa,
+                             [&](uint32_t v, uint32_t n) { bw.put(v, n); return true; });
+                bw.finish();
+            }
+
+            // ---- 3. complete the last owned byte with the next tile's leading bits (at most 7) ---------
+            // Bytes are owned by the tile that holds their first bit.  Runs concurrently with the packing
+            // above: it only ORs into bits at or after `end`.
+            const uint64_t limit = (end + 7) & ~7ull;                // first bit NOT owned by this tile
+            if (tid == 0 && fits && (end & 7u) && !(last_tile && a.strips_avail == a.strips_owned)) {
+                uint32_t pos = (uint32_t)(end - (w0 << 5));
+                const uint32_t lim = (uint32_t)(limit - (w0 << 5));
+                uint32_t st = strip0 + nstrips;                      // raster successor of the tile's last block
+                int hprev = (int)recs[st - 1].last_dc;
+                uint32_t lb = 0;
+                for (int n = 0; n < 2 && pos < lim && st < a.strips_avail; ++n) {
+                    const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
+                    const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
+                    uint32_t hlo = 0, hhi = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t wb = i * 4 + k;
-                    if (wb >= wb0 && wb < wb1) {
-                        const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
-                        if (pos < a.out_capacity) out[pos] = byte;
-                        ++pos;
-                        if (byte == 0xFF) {                         // huffman.c:29-31
-                            if (pos < a.out_capacity) out[pos] = 0x00;
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t q = src[i];
+                        stage[i] = q;
+                        if (i < 8) hlo |= nonzero_nibble(q) << (4 * i);
+                        else hhi |= nonzero_nibble(q) << (4 * (i - 8));
+                    }
+                    hlo &= ~1u;
+                    const int hdc = (int)(int8_t)(src[0] & 0xFFu);
+                    const uint32_t hinfo = a.blkinfo[b];
+                    encode_block(stage_sa, hdc, hprev, (int)((hinfo >> 16) & 63u), hlo, hhi, sym_sa, dc_sa,
+                                 [&](uint32_t v, uint32_t nb) {
+                                     put_clipped(win_sa, pos, lim, v, nb);
+                                     return pos < lim;
+                                 });
+                    hprev = hdc;
+                    if (++lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
+                }
+            }
+            __syncthreads();
+
+            K2_TRACE(t, 4);
+            // ---- 4. count the 0xFF bytes this tile owns and publish the count ---------------------------
+            // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
+            mine.t = t;
+            mine.w0 = w0;
+            mine.B0 = (begin + 7) >> 3;
+            mine.B1 = fits ? (end + 7) >> 3 : mine.B0;
+            const uint32_t wb0 = (uint32_t)(mine.B0 - 4 * w0), wb1 = (uint32_t)(mine.B1 - 4 * w0);   // window byte range
+            const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;                                // window word range
+            uint32_t ffs = 0;
+            for (uint32_t i = wfirst + tid; i < wlast; i += K2_THREADS) ffs += count_ff_bytes(masked_word(win, i, wb0, wb1));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ffs += __shfl_xor_sync(0xffffffffu, ffs, o);
+            if (lane == 0) s_warp[warp] = ffs;
+            __syncthreads();
+            mine.tile_ff = 0;
+#pragma unroll
+            for (int w = 0; w < K2_WARPS; ++w) mine.tile_ff += s_warp[w];
+            if (tid == 0) {
+                st_volatile_u64(a.ff_agg + t, LB_VALID | mine.tile_ff);
+                // next ticket; its round trip overlaps the write-out below (static launches: one tile per CTA)
+                ticket = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : ~0ull;
+            }
+            K2_TRACE(t, 5);
+        }
+
+        // ---- 5. the previously packed tile: stuffed-zero look-back, then write its bytes ---------------
+        // (after the last ticket, or with one tile per CTA, this is an extra round that only writes)
+        const PendingTile w = pend;
+        if (w.t != ~0ull) {
+            const uint32_t *win = k2_smem_words + (cur ^ 1) * WIN_WORDS;
+            const int img = (int)(w.t / (uint64_t)a.tiles), tile = (int)(w.t - (uint64_t)img * a.tiles);
+            uint64_t *ff_incl = a.ff_incl + (uint64_t)img * groups;
+            const uint64_t ff_excl = lookback_grouped(a.ff_agg + (uint64_t)img * a.tiles, ff_incl, tile, a.err, s_scratch);
+            if (tid == 0) {
+                if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(ff_incl + tile / LB_GROUP, LB_VALID | (ff_excl + w.tile_ff));
+                s_carry = 0;
+                if (tile == a.tiles - 1) {
+                    const uint64_t size = w.B1 - origin + ff_excl + w.tile_ff;
+                    a.image_bytes[img] = size;
+                    if (a.count == 1) {
+                        a.scan_offsets[0] = 0;
+                        a.scan_offsets[1] = size;
+                    }
+                    if (size > a.out_capacity) atomicOr(a.err, a.count == 1 ? ERRBIT_OUTPUT : ERRBIT_WORKSPACE);
+                }
+            }
+            __syncthreads();
+            K2_TRACE(w.t, 6);
+            const uint32_t wb0 = (uint32_t)(w.B0 - 4 * w.w0), wb1 = (uint32_t)(w.B1 - 4 * w.w0);
+            const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;
+            uint8_t *out = a.out + (uint64_t)img * a.out_slot;
+            const uint64_t out_base = (w.B0 - origin) + ff_excl;      // output index of window byte wb0
+            for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
+                const uint32_t i = i0 + tid;
+                const uint32_t v = i < wlast ? masked_word(win, i, wb0, wb1) : 0u;
+                const uint32_t cnt = count_ff_bytes(v);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                if (lane == 31) s_warp[warp] = incl;
+                __syncthreads();
+                uint32_t before = s_carry + incl - cnt;
+                uint32_t round_total = 0;
+#pragma unroll
+                for (int ww = 0; ww < K2_WARPS; ++ww) {
+                    const uint32_t ws = s_warp[ww];
+                    if (ww < warp) before += ws;
+                    round_total += ws;
+                }
+                if (i < wlast) {
+                    const uint32_t raw = win[i];
+                    uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t wb = i * 4 + k;
+                        if (wb >= wb0 && wb < wb1) {
+                            const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
+                            if (pos < a.out_capacity) out[pos] = byte;
                             ++pos;
+                            if (byte == 0xFF) {                         // huffman.c:29-31
+                                if (pos < a.out_capacity) out[pos] = 0x00;
+                                ++pos;
+                            }
                         }
                     }
                 }
+                __syncthreads();
+                if (tid == 0) s_carry += round_total;
+                __syncthreads();
             }
-            __syncthreads();
-            if (tid == 0) s_carry += round_total;
-            __syncthreads();
+            K2_TRACE(w.t, 7);
         }
-        K2_TRACE(7);
+        if (!have_tile) break;
+        pend = mine;
+        cur ^= 1;
         if (tid == 0) s_next_tile = ticket;
-        __syncthreads();                                          // shared state is reused by the next tile
     }
 }
 

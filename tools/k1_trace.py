@@ -1,0 +1,34 @@
+"""Tuning aid: per-warp timeline of the fused block kernel (run with JPEGB200_K1_TRACE=1 set by this script)."""
+import os, sys
+os.environ["JPEGB200_K1_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("JPEGB200_LIB", os.path.join(ROOT, "jpeg_image_compression_b200", "libjpegb200_trace.so"))   # make -C .../csrc trace
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import jpeg_image_compression_b200 as jb
+from jpeg_image_compression_b200._lib import check
+
+enc = jb.DeviceEncoder(0)
+w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3840, 2160)
+d = enc.synth(w, h, 1, 1, 20)
+enc.set_profiling(True)
+for _ in range(6):
+    enc.encode_device(d, w, h, 1)
+torch.cuda.synchronize()
+print("kernel times (events):", enc.kernel_times())
+strips = ((w + 255) // 256) * ((h + 7) // 8)
+nwarps = min((strips + 7) // 8, 296) * 8
+tr = np.zeros((nwarps, 8), np.uint64)
+check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, nwarps), "trace")
+t = tr.astype(np.int64)
+t0 = t[:, 0].min()
+names = ["entry", "prologue", "tile0", "pre-table", "table", "strip0-late", "exit"]
+print("warps", nwarps, "strips", strips, "span us", (t[:, 6].max() - t0) / 1e3)
+for i, n in enumerate(names):
+    col = t[:, i]
+    ok = col > 0
+    rel = (col[ok] - t0) / 1e3
+    print(f"{n:12s} n={ok.sum():5d} min {rel.min():6.2f} p10 {np.percentile(rel,10):6.2f} median {np.median(rel):6.2f} p90 {np.percentile(rel,90):6.2f} max {rel.max():6.2f}")
+two = np.arange(nwarps) + nwarps < strips
+life = (t[:, 6] - t[:, 0]) / 1e3
+print(f"warp life: two-strip warps median {np.median(life[two]):.2f}  one-strip warps median {np.median(life[~two]) if (~two).any() else 0:.2f}")

@@ -1,13 +1,15 @@
 """Tuning aid: phase timeline of the fused entropy kernel (run with JPEGB200_K2_TRACE=1)."""
 import os, sys
 os.environ["JPEGB200_K2_TRACE"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("JPEGB200_LIB", os.path.join(ROOT, "jpeg_image_compression_b200", "libjpegb200_trace.so"))   # make -C .../csrc trace
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import jpeg_image_compression_b200 as jb
 from jpeg_image_compression_b200._lib import check
 
 enc = jb.DeviceEncoder(0)
-w, h = 3840, 2160
+w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3840, 2160)
 d = enc.synth(w, h, 1, 1, 20)
 for _ in range(5):
     enc.encode_device(d, w, h, 1)
@@ -25,3 +27,7 @@ for i, n in enumerate(names):
 for i in range(1, 8):
     d_ = (t[:, i] - t[:, i - 1]) / 1e3
     print(f"phase {names[i-1]:>9s}->{names[i]:<9s}: median {np.median(d_):5.2f} p90 {np.percentile(d_, 90):5.2f} max {d_.max():5.2f}")
+span = (t[:, 7] - t[:, 0]) / 1e3
+print(f"tile life: median {np.median(span):5.2f} p90 {np.percentile(span, 90):5.2f} max {span.max():5.2f}")
+order = np.argsort(t[:, 0])
+print("start order == tile order:", bool((order == np.arange(ntiles)).all()))
