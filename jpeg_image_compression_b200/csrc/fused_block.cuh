@@ -486,6 +486,14 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     }
 
     K1_TRACE(6);
+#ifdef JPEGB200_TRACE
+    {   // slot 7: strips done * 1000 + coefficients this warp re-evaluated on the exact path
+        uint32_t nf = nflag;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
+        if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * K1_WARPS + warp) * 8 + 7] = nf;
+    }
+#endif
 #undef K1_TRACE
     if (flagged_counter) {
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);

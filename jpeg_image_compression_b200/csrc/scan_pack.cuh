@@ -322,32 +322,19 @@ k_scan_pack_stuff(const PackArgs a)
             const bool have = (uint32_t)warp < nstrips && (uint32_t)lane < strip_blocks(my_strip, a.spr, a.bw);
             uint32_t info = 0, mlo = 0, mhi = 0;                     // non-zero map of the block's AC coefficients
             int my_dc = 0;
+            uint4 q[4];
             if (have) {
                 const uint32_t brow = my_strip / a.spr, sx = my_strip - brow * a.spr;
                 const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lane;
                 const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + b * 64);
-                uint4 q[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) q[i] = src[i];
                 info = a.blkinfo[b];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    stage[4 * i] = q[i].x; stage[4 * i + 1] = q[i].y; stage[4 * i + 2] = q[i].z; stage[4 * i + 3] = q[i].w;
-                    const uint32_t m16 = nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) |
-                                         (nonzero_nibble(q[i].w) << 12);
-                    if (i < 2) mlo |= m16 << (16 * i);
-                    else mhi |= m16 << (16 * (i - 2));
-                }
-                mlo &= ~1u;                                          // position 0 is the DC
-                my_dc = (int)(int8_t)(q[0].x & 0xFFu);
             }
-            // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
-            // previous strip's last block for lane 0
-            int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+            int prev_dc = 0;
             if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
 
-            K2_TRACE(t, 1);
-            // ---- 1. tile bit offset: wait-free ---------------------------------------------------------
+            // ---- 1a. tile bit offset, wait-free: the loads go out together with the coefficient loads -----
             // K1 left complete per-strip bit counts (only the image's very first DC symbol is missing: its
             // predictor is a run-time argument), so the offset is a plain sum over the earlier strips of the
             // tile's 1024-tile group (read from the compact copy of the counts, four per load) plus the
@@ -369,12 +356,36 @@ k_scan_pack_stuff(const PackArgs a)
                 }
                 if (tail + tid < hi) part += sbits[tail + tid];
             }
+            uint32_t tile_tot = 0;                                   // warp 0: this lane's strip of the tile
+            if (warp == 0 && (uint32_t)lane < nstrips) tile_tot = recs[strip0 + lane].bits;
+
+            if (have) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    stage[4 * i] = q[i].x; stage[4 * i + 1] = q[i].y; stage[4 * i + 2] = q[i].z; stage[4 * i + 3] = q[i].w;
+                    const uint32_t m16 = nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) |
+                                         (nonzero_nibble(q[i].w) << 12);
+                    if (i < 2) mlo |= m16 << (16 * i);
+                    else mhi |= m16 << (16 * (i - 2));
+                }
+                mlo &= ~1u;                                          // position 0 is the DC
+                my_dc = (int)(int8_t)(q[0].x & 0xFFu);
+            }
+            // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
+            // previous strip's last block for lane 0 (fetched above)
+            {
+                const int up = __shfl_up_sync(0xffffffffu, my_dc, 1);
+                if (lane != 0) prev_dc = up;
+            }
+
+            K2_TRACE(t, 1);
+            // ---- 1b. finish the tile bit offset ----------------------------------------------------------
             if (tid == 0) part += g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (lane == 0) s_scratch[warp] = part;
             if (warp == 0) {
-                uint32_t tot = (uint32_t)lane < nstrips ? recs[strip0 + lane].bits : 0u;
+                uint32_t tot = tile_tot;
                 if (tile == 0 && lane == 0) tot += fix0;
                 uint32_t incl = tot;
 #pragma unroll

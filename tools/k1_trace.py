@@ -27,8 +27,18 @@ print("warps", nwarps, "strips", strips, "span us", (t[:, 6].max() - t0) / 1e3)
 for i, n in enumerate(names):
     col = t[:, i]
     ok = col > 0
+    if not ok.any():
+        continue
     rel = (col[ok] - t0) / 1e3
     print(f"{n:12s} n={ok.sum():5d} min {rel.min():6.2f} p10 {np.percentile(rel,10):6.2f} median {np.median(rel):6.2f} p90 {np.percentile(rel,90):6.2f} max {rel.max():6.2f}")
+nf = t[:, 7]
+two_ = np.arange(nwarps) + nwarps < strips
+for name, grp in (("two-strip", two_), ("one-strip", ~two_)):
+    for lo, hi in ((0, 0), (1, 1), (2, 2), (3, 99)):
+        sel = grp & (nf >= lo) & (nf <= hi)
+        if sel.any():
+            life = (t[sel, 6] - t[sel, 0]) / 1e3
+            print(f"{name} warps with {lo}..{hi} exact-path coefficients: n={sel.sum():5d} life median {np.median(life):6.2f} p90 {np.percentile(life, 90):6.2f} max {life.max():6.2f}")
 two = np.arange(nwarps) + nwarps < strips
 life = (t[:, 6] - t[:, 0]) / 1e3
 print(f"warp life: two-strip warps median {np.median(life[two]):.2f}  one-strip warps median {np.median(life[~two]) if (~two).any() else 0:.2f}")
