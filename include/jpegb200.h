@@ -178,6 +178,14 @@ int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb200_batch *ba
                                  uint8_t *d_scan, uint64_t scan_capacity,
                                  uint64_t *d_scan_offsets, void *cuda_stream);
 
+/* Same, but the output holds complete JFIF files: for every image the 328-byte header that
+ * saveJPEGGrayscale writes (src/io/jpeg_handler.c:220-233), its scan (:252) and the EOI marker (:262),
+ * back to back; d_file_offsets is uint64[count+1].  One D2H copy then yields `count` finished .jpg
+ * files with no per-file host formatting.  Capacity: scan bytes + 330 per image. */
+int jpegb200_encode_batch_files_device(jpegb200_encoder *enc, const jpegb200_batch *batch,
+                                       uint8_t *d_files, uint64_t capacity,
+                                       uint64_t *d_file_offsets, void *cuda_stream);
+
 /* Device error word (sticky until read; 0 = ok, else a JPEGB200_ERR_*); synchronises the stream. */
 int jpegb200_encoder_status(jpegb200_encoder *enc, void *cuda_stream);
 

@@ -322,7 +322,7 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
 
 // ---- kernel launches (optionally bracketed by cudaEvents for per-kernel timing) -----------
 
-enum KernelId { KID_BLOCK = 0, KID_ENTROPY = 1, KID_LAYOUT = 2, KID_COMPACT = 3 };
+enum KernelId { KID_BLOCK = 0, KID_ENTROPY = 1, KID_LAYOUT = 2, KID_COMPACT = 3, KID_FRAME = 4 };
 
 struct TimedLaunch {
     jpegb200_encoder *enc;
@@ -410,31 +410,41 @@ static void harvest_events(jpegb200_encoder *enc)
     enc->event_kernel.clear();
 }
 
+// files: frame every scan with the JFIF header and EOI (d_scan then receives complete files)
 static int encode_launch(jpegb200_encoder *enc, uint8_t *d_scan, uint64_t scan_capacity, uint64_t *d_scan_offsets,
-                         cudaStream_t st)
+                         cudaStream_t st, bool files = false)
 {
     int rc = 0;
     enc->launches = 0;
     enc->stripe_ready = false;
     PackArgs &a = enc->args;
     a.scan_offsets = d_scan_offsets;
+    const uint64_t lead = files ? 328 : 0, extra = files ? 330 : 0;
     if (a.count == 1) {
-        a.out = d_scan;
-        a.out_capacity = scan_capacity;
+        a.out = d_scan + lead;
+        a.out_capacity = scan_capacity > extra ? scan_capacity - extra : 0;
     }
     if ((rc = launch_block_kernel(enc, st))) return rc;
     if ((rc = launch_entropy(enc, st))) return rc;
     if (a.count > 1) {
         {
             TimedLaunch t(enc, st, KID_LAYOUT);
-            k_layout<<<1, 1024, 0, st>>>(a.image_bytes, d_scan_offsets, a.count, scan_capacity, a.err);
+            k_layout<<<1, 1024, 0, st>>>(a.image_bytes, d_scan_offsets, a.count, scan_capacity, a.err, extra);
         }
         {
             TimedLaunch t(enc, st, KID_COMPACT);
             const unsigned gx = (unsigned)std::min<uint64_t>((a.out_slot / 16 + 255) / 256, 64);
             k_compact<<<dim3(gx, (unsigned)a.count), 256, 0, st>>>(a.out, a.out_slot, a.image_bytes, d_scan_offsets, d_scan,
-                                                                   scan_capacity);
+                                                                   scan_capacity, lead);
         }
+        JB_CUDA(cudaGetLastError());
+    }
+    if (files) {
+        JfifHeaderBytes hb;
+        jpegb200_jfif_header(enc->geom.w, enc->geom.h, hb.b);
+        TimedLaunch t(enc, st, KID_FRAME);
+        k_frame_files<<<(unsigned)a.count, 128, 0, st>>>(hb, a.image_bytes, d_scan_offsets, d_scan, scan_capacity,
+                                                         a.count == 1 ? 1 : 0, a.err);
         JB_CUDA(cudaGetLastError());
     }
     return JPEGB200_OK;
@@ -537,6 +547,20 @@ extern "C" int jpegb200_encode_batch_device(jpegb200_encoder *enc, const jpegb20
     int rc = prepare(enc, batch->d_rgb, batch->width, batch->height, batch->count, batch->image_stride, 0);
     if (rc) return rc;
     return encode_launch(enc, d_scan, scan_capacity, d_scan_offsets, st);
+}
+
+// Same, but the output holds complete JFIF files (header + scan + EOI per image), back to back.
+extern "C" int jpegb200_encode_batch_files_device(jpegb200_encoder *enc, const jpegb200_batch *batch, uint8_t *d_files,
+                                                  uint64_t capacity, uint64_t *d_file_offsets, void *cuda_stream)
+{
+    if (!enc || !batch || !d_files || !d_file_offsets) {
+        g_last_error = "bad argument";
+        return JPEGB200_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int rc = prepare(enc, batch->d_rgb, batch->width, batch->height, batch->count, batch->image_stride, 0);
+    if (rc) return rc;
+    return encode_launch(enc, d_files, capacity, d_file_offsets, st, true);
 }
 
 // Device error word (sticky until read): 0 = ok, else a JPEGB200_ERR_*.  Synchronises the stream.

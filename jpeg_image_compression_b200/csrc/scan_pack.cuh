@@ -573,9 +573,11 @@ k_scan_pack_stuff(const PackArgs a)
 
 // ---------------------------------------------------------------------------------
 // batch mode: exclusive scan of the stuffed image sizes -> scan_offsets[count+1]  (one CTA)
+// `extra`: bytes that frame every image in the output besides its scan (0, or 330 in files mode: the
+// 328-byte JFIF header and the 2-byte EOI marker)
 __global__ void __launch_bounds__(1024)
 k_layout(const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ scan_offsets, const int count,
-         const uint64_t scan_capacity, uint32_t *err)
+         const uint64_t scan_capacity, uint32_t *err, const uint64_t extra)
 {
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
@@ -584,7 +586,7 @@ k_layout(const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ scan_o
     __syncthreads();
     for (int base = 0; base < count; base += 1024) {
         const int i = base + tid;
-        const uint64_t v = i < count ? image_bytes[i] : 0;
+        const uint64_t v = i < count ? image_bytes[i] + extra : 0;
         uint64_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -618,11 +620,12 @@ k_layout(const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ scan_o
 // with a funnel shift; the few head / tail bytes are copied one by one.
 __global__ void __launch_bounds__(256)
 k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const uint64_t *__restrict__ image_bytes,
-          const uint64_t *__restrict__ scan_offsets, uint8_t *__restrict__ scan, const uint64_t scan_capacity)
+          const uint64_t *__restrict__ scan_offsets, uint8_t *__restrict__ scan, const uint64_t scan_capacity,
+          const uint64_t lead)
 {
     const int img = blockIdx.y;
-    const uint64_t n = image_bytes[img], dst0 = scan_offsets[img];
-    if (dst0 + n > scan_capacity) return;                        // flagged by k_layout
+    const uint64_t n = image_bytes[img], dst0 = scan_offsets[img] + lead;   // lead: room for the file header
+    if (scan_offsets[img + 1] > scan_capacity) return;           // flagged by k_layout
     const uint8_t *src = slots + (uint64_t)img * slot_stride;
     uint8_t *dst = scan + dst0;
     const uint64_t head = min(n, (uint64_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));   // bytes up to dst alignment
@@ -634,6 +637,33 @@ k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const u
     uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
     const uint32_t sh = (uint32_t)head * 8u;                     // src word phase relative to dst words (head < 4)
     for (uint64_t j = tid; j < nwords; j += nthreads) d32[j] = __funnelshift_r(s32[j], s32[j + 1], sh);
+}
+
+// files mode: frame every image's scan with the JFIF header (jpeg_handler.c:220-233; the 328 bytes are
+// the same for all images of a batch and travel as a kernel argument) and the EOI marker
+// (jpeg_handler.c:262).  One CTA per image.  single: the count == 1 path, where K2 wrote the scan in
+// place at offset 328 and left scan_offsets = {0, scan bytes}.
+struct JfifHeaderBytes {
+    uint8_t b[328];
+};
+
+__global__ void __launch_bounds__(128)
+k_frame_files(const JfifHeaderBytes header, const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ file_offsets,
+              uint8_t *__restrict__ files, const uint64_t capacity, const int single, uint32_t *err)
+{
+    const int img = blockIdx.x;
+    const uint64_t n = image_bytes[img];
+    const uint64_t begin = single ? 0 : file_offsets[img], end = single ? n + 330 : file_offsets[img + 1];
+    if (single && threadIdx.x == 0) {
+        file_offsets[1] = end;
+        if (end > capacity) atomicOr(err, ERRBIT_OUTPUT);
+    }
+    if (end > capacity) return;
+    for (int i = threadIdx.x; i < 328; i += blockDim.x) files[begin + i] = header.b[i];
+    if (threadIdx.x == 0) {
+        files[begin + 328 + n] = 0xFF;
+        files[begin + 329 + n] = 0xD9;
+    }
 }
 
 }  // namespace jb

@@ -70,6 +70,28 @@ class DeviceEncoder:
                                                     offsets.data_ptr(), self._stream()), "encode_batch_device")
         return scan, offsets
 
+    def encode_files_device(self, d_rgb, w: int, h: int, count: int = 1, image_stride: int = 0, files=None, offsets=None):
+        """Like encode_device, but the output tensor holds complete JFIF files (header + scan + EOI per
+        image, back to back; offsets[count+1]) -- jpegb200_encode_batch_files_device."""
+        if files is None or offsets is None:
+            files, offsets = self._ensure_out(self.scan_capacity(w, h, count) + 330 * count, count)
+        b = Batch(d_rgb.data_ptr(), w, h, count, image_stride)
+        check(self.lib.jpegb200_encode_batch_files_device(self.handle, C.byref(b), files.data_ptr(), files.numel(),
+                                                          offsets.data_ptr(), self._stream()), "encode_batch_files_device")
+        return files, offsets
+
+    def encode_batch_files(self, rgbs: np.ndarray) -> list:
+        """Host RGB (n,h,w,3) -> list of complete .jpg file images, framed on the device."""
+        t = self.torch
+        rgbs = np.ascontiguousarray(rgbs, np.uint8)
+        n, h, w, _ = rgbs.shape
+        d = t.from_numpy(rgbs).to(f"cuda:{self.device}")
+        files, offsets = self.encode_files_device(d, w, h, n)
+        self.status()
+        offs = offsets[: n + 1].cpu().numpy()
+        data = files[: int(offs[n])].cpu().numpy().tobytes()
+        return [data[int(offs[i]): int(offs[i + 1])] for i in range(n)]
+
     def status(self):
         check(self.lib.jpegb200_encoder_status(self.handle, self._stream()), "encoder_status")
 
@@ -131,7 +153,7 @@ class DeviceEncoder:
         calls = (C.c_uint64 * 8)()
         check(self.lib.jpegb200_encoder_kernel_times(self.handle, ms, calls, int(reset)), "kernel_times")
         return {"ms": list(ms), "calls": [int(c) for c in calls],
-                "names": ["fused_block", "scan_pack_stuff", "batch_layout", "batch_compact", "", "", "", ""]}
+                "names": ["fused_block", "scan_pack_stuff", "batch_layout", "batch_compact", "frame_files", "", "", ""]}
 
     def coefficients(self, nblocks: int) -> np.ndarray:
         out = np.empty((nblocks, 64), np.int16)

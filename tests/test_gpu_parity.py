@@ -449,3 +449,25 @@ def test_two_streams_many_tiles_no_deadlock(synth_hashes):
         assert n == e["scan_bytes"] and hashlib.sha256(s[:n].cpu().numpy().tobytes()).hexdigest() == e["scan_sha256"]
     for enc_ in encs:
         enc_.close()
+
+
+def test_files_framed_on_device(enc, oracle, golden, golden_names):
+    """jpegb200_encode_batch_files_device: header + scan + EOI assembled on the device equal the files
+    the reference writes (golden /file fixtures), for single images and inside a batch."""
+    for name in golden_names:
+        rgb = golden[f"{name}/rgb"]
+        files = enc.encode_batch_files(rgb[None])
+        assert files[0] == golden[f"{name}/file"].tobytes(), name
+    imgs = np.stack([oracle.synth_rgb(203, 77, s, 30) for s in range(9)])          # ragged size, odd offsets
+    files = enc.encode_batch_files(imgs)
+    header = oracle.jfif_header(203, 77)
+    for i in range(9):
+        assert files[i] == header + oracle.encode_scan(imgs[i]) + b"\xff\xd9", i
+    # too small an output buffer is reported, not overrun
+    import torch
+    d = torch.from_numpy(imgs).cuda()
+    small = torch.zeros(1000, dtype=torch.uint8, device="cuda")
+    offs = torch.zeros(10, dtype=torch.int64, device="cuda")
+    enc.encode_files_device(d, 203, 77, 9, files=small, offsets=offs)
+    with pytest.raises(jb.JpegB200Error):
+        enc.status()
