@@ -158,6 +158,11 @@ const char  *jpegb200_last_error(void);
 jpegb200_encoder *jpegb200_encoder_create(int device);
 void         jpegb200_encoder_destroy(jpegb200_encoder *enc);
 int          jpegb200_encoder_set_dct_mode(jpegb200_encoder *enc, int dct_mode);
+/* Workspace hint: expected packed bytes per 8x8 block, averaged over any 256 consecutive blocks
+ * (default 24; up to 32 the entropy kernel runs with its small shared-memory bit windows, above
+ * that with the worst-case ones: 184 covers every possible input).  It also sizes the per-image
+ * slots of batch mode.  Too small a value is never silent: the encode reports
+ * JPEGB200_ERR_WORKSPACE and can be re-run with a larger one. */
 int          jpegb200_encoder_set_bytes_per_block(jpegb200_encoder *enc, int bytes_per_block);
 
 /* Description of one launch: `count` images of identical geometry, image i starting

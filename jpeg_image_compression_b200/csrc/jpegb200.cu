@@ -347,7 +347,8 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
     const Geom &g = enc->geom;
     const uint64_t want = (g.total_strips + K1_WARPS - 1) / K1_WARPS;
-    const int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
+    int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
+    if (const char *e = getenv("JPEGB200_K1_GRID")) grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, atoi(e)));   // tuning aid
     if (getenv("JPEGB200_K1_TRACE")) {              // tuning aid: per-warp timestamps
         if (int rc = enc->trace1.reserve((uint64_t)grid * K1_WARPS * 64)) return rc;
         JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * K1_WARPS * 64, st));
@@ -366,12 +367,12 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     return JPEGB200_OK;
 }
 
-// K2: fused scan + pack + stuff; persistent CTAs (never more than can be co-resident: tiles wait
-// on their predecessors) taking tiles of 4 strips in increasing order
+// K2: fused scan + pack + stuff over tiles of 8 strips; one CTA per tile if that is a single wave,
+// otherwise as many persistent CTAs as can be co-resident, drawing tiles by ticket
 static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {
     const PackArgs &a = enc->args;
-    // window size: 64 bytes per block on average unless the caller asked for more workspace
+    // window size: 32 bytes per block on average over a tile unless the caller asked for more workspace
     const bool small = enc->bytes_per_block * 8 <= K2_SMALL_BLOCK_BITS;
     const int smem = small ? k2_smem(K2_SMALL_BLOCK_BITS) : k2_smem(K2_MAX_BLOCK_BITS);
     int &per_sm = enc->k2_ctas_per_sm[small ? 0 : 1];
