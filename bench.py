@@ -307,6 +307,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         g1 = capture(1)
         single_stream_ms = timed(args.steps, g1) / args.steps
 
+    # ---- sensitivity rows of SURVEY.md 8(d): the same workload at amp=0 (smooth) and amp=64 (entropy-heavy) ----
+    sensitivity = None
+    if args.workload == "uhd4k" and world == 1 and use_graph and not args.no_sensitivity:
+        sensitivity = {}
+        main_inputs, main_graph = inputs, graph
+        for amp in (0, 64):
+            inputs = [enc.synth(w, h, per_step, seed0 + i * per_step, amp) for i in range(ring)]
+            for e in encs:
+                for i in range(ring):
+                    step(i, e)
+            torch.cuda.synchronize()
+            for e in encs:
+                e.status()
+            sb = sum(int(o[per_step].item()) for _, o in outs) / ring
+            graph = capture(nstreams)
+            n = max(ring, min(args.steps, 400))
+            ms = timed(n)
+            for e in encs:
+                e.status()
+            sensitivity[f"amp{amp}"] = {"value": round(px_step * n / (ms * 1e-3) / 1e6, 1), "unit": UNIT,
+                                        "scan_bytes_per_step": int(sb), "steps": n}
+        inputs, graph = main_inputs, main_graph
+
     # ---- per-kernel time of the dominant kernel (cudaEvents on the launching stream) -----------
     enc.set_profiling(True)
     enc.kernel_times(reset=True)
@@ -426,7 +449,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                          f"({ring_bytes / 1e6:.0f} MB > 126 MB L2), no flush needed",
                        "cuda_graph": bool(graph is not None), "scan_bytes_per_step": int(mean_scan),
                        "encoder_streams": nstreams,
-                       "single_stream_ms_per_step": round(single_stream_ms, 5) if single_stream_ms else None},
+                       "single_stream_ms_per_step": round(single_stream_ms, 5) if single_stream_ms else None,
+                       "sensitivity": sensitivity},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
@@ -448,6 +472,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="encoder handles / streams with independent images in flight")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sensitivity", action="store_true", help="skip the amp=0 / amp=64 rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -185,10 +185,12 @@ static void emit(orc_symbol *out, size_t *n, uint8_t sym, uint16_t amp, uint8_t 
     ++*n;
 }
 
-size_t orc_rle(const int16_t *zz, size_t nblocks, orc_symbol *out)
+/* the chain of rle.c:59-124 over `nblocks` blocks, starting from predictor *pred_io (0 at the start
+ * of an image, rle.c:59) and leaving the last block's DC there */
+static size_t rle_chain(const int16_t *zz, size_t nblocks, orc_symbol *out, int16_t *pred_io)
 {
     size_t n = 0;
-    int16_t pred = 0;                                      /* rle.c:59: one chain per image */
+    int16_t pred = *pred_io;
     for (size_t b = 0; b < nblocks; ++b) {
         const int16_t *c = zz + b * 64;
         const int16_t diff = (int16_t)(c[0] - pred);       /* rle.c:68-70 */
@@ -210,7 +212,14 @@ size_t orc_rle(const int16_t *zz, size_t nblocks, orc_symbol *out)
         }
         if (last < 63) emit(out, &n, 0x00, 0, 0);          /* EOB, rle.c:121-123 */
     }
+    *pred_io = pred;
     return n;
+}
+
+size_t orc_rle(const int16_t *zz, size_t nblocks, orc_symbol *out)
+{
+    int16_t pred = 0;                                      /* rle.c:59: one chain per image */
+    return rle_chain(zz, nblocks, out, &pred);
 }
 
 /* ---- stage 7: canonical Huffman + bit packing (huffman.c:26-193) --------- */
@@ -274,11 +283,11 @@ static void sink_flush(bitsink *s)                         /* huffman.c:65-81: Z
     s->fill = 0;
 }
 
-size_t orc_huffman(const orc_symbol *sym, size_t nsym, size_t nblocks, uint8_t *out)
+/* huffman.c:139-191 for a run of blocks, appending to an open bit sink (no flush) */
+static void huffman_blocks(bitsink *sink, const hcode dc[16], const hcode ac[256], const orc_symbol *sym, size_t nsym,
+                           size_t nblocks)
 {
-    hcode dc[16], ac[256];
-    huffman_tables(dc, ac);
-    bitsink s = {out, 0, 0, 0};
+    bitsink s = *sink;
     size_t i = 0;
     for (size_t b = 0; b < nblocks && i < nsym; ++b) {     /* huffman.c:139-141 */
         const orc_symbol d = sym[i++];                     /* huffman.c:145-153 */
@@ -293,6 +302,15 @@ size_t orc_huffman(const orc_symbol *sym, size_t nsym, size_t nblocks, uint8_t *
             done += (a.symbol == 0xF0) ? 16 : ((a.symbol >> 4) & 15) + 1;
         }
     }
+    *sink = s;
+}
+
+size_t orc_huffman(const orc_symbol *sym, size_t nsym, size_t nblocks, uint8_t *out)
+{
+    hcode dc[16], ac[256];
+    huffman_tables(dc, ac);
+    bitsink s = {out, 0, 0, 0};
+    huffman_blocks(&s, dc, ac, sym, nsym, nblocks);
     sink_flush(&s);
     return s.size;
 }
@@ -391,13 +409,14 @@ static uint32_t tri(uint32_t t, uint32_t period)
     return d * 255u / period;
 }
 
-void orc_synth_rgb(int w, int h, uint32_t seed, int amp, uint8_t *rgb)
+/* rows [y0, y0 + rows) of the w-wide synthetic image, written from rgb[0] on */
+static void synth_rows(int w, int y0, int rows, uint32_t seed, int amp, uint8_t *rgb)
 {
     static const int offset[3] = {10, 0, -10};
     const uint32_t span = (uint32_t)(2 * amp + 1);
-    for (int y = 0; y < h; ++y) {
+    for (int y = 0; y < rows; ++y) {
         for (int x = 0; x < w; ++x) {
-            const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;
+            const uint32_t ux = (uint32_t)x, uy = (uint32_t)(y0 + y);
             const uint32_t base = (tri(ux + 2u * uy, 419u) + tri(3u * ux + (1u << 20) - uy, 1021u) +
                                    tri(uy, 173u) + tri(ux, 67u)) / 4u;
             for (int c = 0; c < 3; ++c) {
@@ -413,4 +432,91 @@ void orc_synth_rgb(int w, int h, uint32_t seed, int amp, uint8_t *rgb)
             }
         }
     }
+}
+
+void orc_synth_rgb(int w, int h, uint32_t seed, int amp, uint8_t *rgb) { synth_rows(w, 0, h, seed, amp, rgb); }
+
+/* ---- streaming encode of a synthetic image of any size --------------------
+ * For images beyond the reference's int-indexed buffers (> 715 Mpixel: bmp_handler.c:78,119,
+ * converter.c:39 overflow) the whole-image functions above would need tens of GB.
+ * This walks the image in bands of whole block rows: a band's pixels are generated and taken
+ * through stages 1-5 (position-independent), `threads` bands at a time in parallel; the entropy
+ * stages then consume the bands in order with the DC predictor (rle.c:59-70) and the bit
+ * accumulator (huffman.c:35-62) carried across bands.  Same arithmetic, same order, size_t
+ * indices.  tests/test_oracle.py checks it against orc_encode_scan and the reference's hashes. */
+#include <pthread.h>
+
+typedef struct {
+    int w, y0, rows;
+    uint32_t seed;
+    int amp;
+    int16_t *zz;          /* out: (wp/8)*(rows_p/8)*64 coefficients */
+    size_t nblocks;
+    int failed;
+} band_job;
+
+static void *band_worker(void *arg)
+{
+    band_job *j = (band_job *)arg;
+    uint8_t *rgb = (uint8_t *)malloc((size_t)j->w * (size_t)j->rows * 3u);
+    if (!rgb) { j->failed = 1; return NULL; }
+    synth_rows(j->w, j->y0, j->rows, j->seed, j->amp, rgb);
+    j->failed = orc_coefficients(rgb, j->w, j->rows, j->zz) != j->nblocks;   /* ragged last band: rows replicate, converter.c:31 */
+    free(rgb);
+    return NULL;
+}
+
+size_t orc_encode_scan_synth_banded(int w, int h, uint32_t seed, int amp, int band_block_rows, int threads, uint8_t **out)
+{
+    *out = NULL;
+    if (w <= 0 || h <= 0 || band_block_rows <= 0 || threads <= 0 || threads > 256) return 0;
+    const int bw = orc_pad8(w) / 8, band_px = band_block_rows * 8;
+    const int nbands = (h + band_px - 1) / band_px;
+    const size_t band_blocks = (size_t)bw * (size_t)band_block_rows;
+    hcode dc[16], ac[256];
+    huffman_tables(dc, ac);
+    size_t cap = (size_t)bw * (size_t)(orc_pad8(h) / 8) * 24u + 4096u;   /* grown on demand */
+    uint8_t *buf = (uint8_t *)malloc(cap);
+    int16_t *zz = (int16_t *)malloc((size_t)threads * band_blocks * 64u * sizeof(int16_t));
+    orc_symbol *sym = (orc_symbol *)malloc(band_blocks * 64u * sizeof(orc_symbol));
+    band_job *jobs = (band_job *)calloc((size_t)threads, sizeof(band_job));
+    pthread_t *tid = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    int ok = buf && zz && sym && jobs && tid;
+    bitsink s = {buf, 0, 0, 0};
+    int16_t pred = 0;
+    for (int b0 = 0; ok && b0 < nbands; b0 += threads) {
+        const int n = nbands - b0 < threads ? nbands - b0 : threads;
+        for (int i = 0; i < n; ++i) {
+            band_job *j = &jobs[i];
+            j->w = w; j->y0 = (b0 + i) * band_px;
+            j->rows = h - j->y0 < band_px ? h - j->y0 : band_px;
+            j->seed = seed; j->amp = amp;
+            j->zz = zz + (size_t)i * band_blocks * 64u;
+            j->nblocks = (size_t)bw * (size_t)(orc_pad8(j->rows) / 8);
+            j->failed = 0;
+            if (pthread_create(&tid[i], NULL, band_worker, j) != 0) { j->failed = 1; tid[i] = 0; band_worker(j); }
+        }
+        for (int i = 0; i < n; ++i) {
+            if (tid[i]) pthread_join(tid[i], NULL);
+            tid[i] = 0;
+        }
+        for (int i = 0; ok && i < n; ++i) {
+            const band_job *j = &jobs[i];
+            if (j->failed) { ok = 0; break; }
+            const size_t nsym = rle_chain(j->zz, j->nblocks, sym, &pred);
+            if (s.size + nsym * 8u + 64u > cap) {          /* <= 27 bits per symbol, doubled by stuffing at worst */
+                cap = (s.size + nsym * 8u + 64u) * 2u;
+                uint8_t *nb = (uint8_t *)realloc(buf, cap);
+                if (!nb) { ok = 0; break; }
+                buf = nb;
+                s.dst = buf;
+            }
+            huffman_blocks(&s, dc, ac, sym, nsym, j->nblocks);
+        }
+    }
+    if (ok) sink_flush(&s);
+    free(zz); free(sym); free(jobs); free(tid);
+    if (!ok) { free(buf); return 0; }
+    *out = buf;
+    return s.size;
 }

@@ -72,6 +72,14 @@ size_t orc_jfif_header(int w, int h, uint8_t out[328]);
 /* Synthetic workload generator of SURVEY.md section 8(d) (integer only). */
 void   orc_synth_rgb(int w, int h, uint32_t seed, int amp, uint8_t *rgb);
 
+/* Streaming encode of the synthetic image (w, h, seed, amp) of ANY size, including those beyond the
+ * reference's int-indexed buffers (> 715 Mpixel): bands of `band_block_rows` block rows
+ * go through stages 1-5 on `threads` threads, the entropy stages consume them in order with the DC
+ * predictor and bit accumulator carried along.  Equals orc_encode_scan(orc_synth_rgb(...)) wherever
+ * that is computable (checked in tests/test_oracle.py).  *out is malloc'd; free with orc_free. */
+size_t orc_encode_scan_synth_banded(int w, int h, uint32_t seed, int amp, int band_block_rows, int threads,
+                                    uint8_t **out);
+
 #ifdef __cplusplus
 }
 #endif

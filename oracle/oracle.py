@@ -66,6 +66,8 @@ class Oracle:
         L.orc_encode_scan.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
         L.orc_encode_scan.restype = sz
         L.orc_free.argtypes = [vp]
+        L.orc_encode_scan_synth_banded.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.orc_encode_scan_synth_banded.restype = sz
         L.orc_jfif_header.argtypes = [C.c_int, C.c_int, vp]
         L.orc_jfif_header.restype = sz
         L.orc_synth_rgb.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, vp]
@@ -153,6 +155,20 @@ class Oracle:
         n = self.lib.orc_encode_scan(rgb.ctypes.data, w, h, C.byref(p))
         try:
             return C.string_at(p.value, n) if n else b""
+        finally:
+            self.lib.orc_free(p)
+
+    def encode_scan_synth_banded(self, w: int, h: int, seed: int = 1, amp: int = 20, band_block_rows: int = 8,
+                                 threads: int = 0) -> bytes:
+        """Streaming encode of the synthetic image of any size (also beyond the reference's 715 Mpixel
+        index limit): orc_encode_scan_synth_banded.  threads=0: all host cores."""
+        import os
+        p = C.c_void_p()
+        n = self.lib.orc_encode_scan_synth_banded(w, h, seed, amp, band_block_rows, threads or (os.cpu_count() or 1), C.byref(p))
+        try:
+            if not p.value:
+                raise MemoryError("orc_encode_scan_synth_banded failed")
+            return C.string_at(p.value, n)
         finally:
             self.lib.orc_free(p)
 

@@ -471,3 +471,21 @@ def test_files_framed_on_device(enc, oracle, golden, golden_names):
     enc.encode_files_device(d, 203, 77, 9, files=small, offsets=offs)
     with pytest.raises(jb.JpegB200Error):
         enc.status()
+
+
+def test_gigapixel_equals_streaming_oracle(enc, oracle):
+    """BASELINE config 5 (32768x32768, beyond the reference's int-indexed buffers): the single-GPU encode of
+    the device-generated image against the oracle's streaming (banded) encode of the same synthetic image --
+    87 MB of scan, byte for byte (SHA-256)."""
+    import torch
+    w = h = 32768
+    d = enc.synth(w, h, 1, 1, 20)
+    scan, offs = enc.encode_device(d, w, h, 1)
+    enc.status()
+    n = int(offs[1].item())
+    got = scan[:n].cpu().numpy().tobytes()
+    del d
+    torch.cuda.empty_cache()
+    want = oracle.encode_scan_synth_banded(w, h, 1, 20, 8, 0)
+    assert n == len(want)
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()

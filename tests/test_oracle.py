@@ -136,3 +136,16 @@ def test_quantized_magnitude_bound(oracle):
                 q = oracle.quantize(oracle.fdct_block(blk).reshape(8, 8))
                 worst = max(worst, int(np.abs(q).max()))
     assert worst <= 95
+
+
+def test_banded_streaming_oracle_equals_whole_image_oracle(oracle, synth_hashes):
+    """orc_encode_scan_synth_banded (the oracle for images beyond the reference's int-index limit,
+    SURVEY.md 8c) walks the image in bands with carried entropy state: it must equal the whole-image
+    oracle for every band size / thread count, and the reference build's hashes at 4K."""
+    for (w, h, seed, amp, rows, threads) in ((200, 120, 3, 20, 1, 1), (203, 77, 5, 30, 2, 3), (64, 8, 1, 0, 8, 4),
+                                            (1283, 725, 9, 20, 4, 8), (7, 9, 2, 64, 1, 2), (257, 1031, 4, 64, 3, 5)):
+        whole = oracle.encode_scan(oracle.synth_rgb(w, h, seed, amp))
+        assert oracle.encode_scan_synth_banded(w, h, seed, amp, rows, threads) == whole, (w, h, rows, threads)
+    e = synth_hashes["3840x2160_seed1_amp20"]
+    b = oracle.encode_scan_synth_banded(3840, 2160, 1, 20, 8, 0)
+    assert len(b) == e["scan_bytes"] and hashlib.sha256(b).hexdigest() == e["scan_sha256"]
