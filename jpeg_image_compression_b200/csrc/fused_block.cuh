@@ -22,13 +22,14 @@
 // Bit-exactness.  The reference sums 64 products sequentially in fp32 with two unfused
 // multiplies per term; replaying that costs ~136 flop/pixel.  Instead the butterfly
 // value T (ideal cosines, FMA) is bracketed: the reference's sum s_ref satisfies
-// |s_ref - g*T| <= kGamma * A with A = sum|p| over the block (DESIGN.md derives the
-// bound: 66u*A for the reference's own roundings, 24u*A for the butterfly's, 1.45e-6*A
-// for the 6-decimal LUT vs ideal cosines, 2^-20*A for the scale/divide roundings;
-// u = 2^-24).  Quantization is monotone in s, so if rounding (T-E)*rk and (T+E)*rk give
-// the same integer that integer IS the reference's; otherwise (about 1e-4 of the
-// coefficients) the lane re-evaluates that one coefficient in the reference's exact
-// operation order (exact_quantized below).  The DC term is an exact integer sum in both
+// |s_ref - g*T| <= kGamma * A with A = sum|p| over the block (DESIGN.md section 3 derives the
+// bound: 65.1u*A for the reference's own roundings, 16u*A for the butterfly's, 15.7u*A
+// for the 6-decimal LUT vs ideal cosines, 6u*A for the scale/divide roundings, 102.8u*A in
+// total with u = 2^-24; the kernel takes the minimum with a mean-separated refinement,
+// u*(17.5*A + 103*Ac + 500), Ac = sum|p - mean|).  Quantization is monotone in s, so if
+// rounding (T-E)*rk and (T+E)*rk give the same integer that integer IS the reference's;
+// otherwise (about 2e-4 of the coefficients) the lane re-evaluates that one coefficient in
+// the reference's exact operation order (exact_quantized below).  The DC term is an exact integer sum in both
 // formulations and is quantized with the reference's own operation sequence.
 #pragma once
 

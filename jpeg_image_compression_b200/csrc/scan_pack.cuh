@@ -5,23 +5,24 @@
 // (rle.c:59-70) and one contiguous MSB-first bit stream (huffman.c:35-62) with a zero byte
 // stuffed after every 0xFF (huffman.c:26-32) and a zero-padded last byte (huffman.c:65-81).
 //
-// K1 leaves, per 32-block strip, a record {bits, first DC, last DC} and per block its bit
-// offset inside the strip, so everything cross-block collapses to two prefix sums:
+// K1 leaves, per 32-block strip, a record {bits, first DC, last DC} (the bit count already includes
+// every DC-difference symbol) and per block its bit offset inside the strip, so everything
+// cross-block collapses to two prefix sums:
 //
 //   tile = 8 consecutive strips (<= 256 blocks), one CTA, warp w <-> strip, lane <-> block
-//   1. warp 0 adds the DC-difference cost of each strip's first block (needs the previous
-//      strip's last DC), sums the tile, publishes the aggregate and obtains the tile's bit
-//      offset by a grouped look-back over the image's earlier tiles (common.cuh);
-//   2. every lane re-derives its block's symbols from the 64 int8 coefficients (only up to
-//      the last non-zero one) and appends code+amplitude bits to a register accumulator that
-//      is flushed word-wise into a shared-memory window (atomicOr only on the two words a
-//      block shares with its neighbours);
+//   1. the lane's coefficients, and the bit counts of the earlier strips, are requested up front; the
+//      tile's bit offset is their plain sum (wait-free; one checkpoint word per 1024 tiles);
+//   2. every lane walks the non-zero coefficients of its block (one table look-up per symbol) and
+//      appends code+amplitude bits to a register accumulator that is OR-reduced word-wise into a
+//      zeroed shared-memory window;
 //   3. bytes are owned by the tile that holds their first bit: the last, partial byte is
 //      completed by encoding the next tile's first block(s) clipped at the byte boundary, the
 //      first partial byte is skipped -- no bits ever cross CTAs through global memory;
-//   4. 0xFF bytes of the tile's byte range are counted, a second look-back gives the number
-//      of stuffed zeros before the tile, and the stuffed bytes go straight to the output.
-// CTAs are persistent and take tiles in increasing order.
+//   4. 0xFF bytes of the tile's byte range are counted and published; a look-back over the earlier
+//      tiles' counts gives the number of stuffed zeros before the tile, and the stuffed bytes go
+//      straight to the output.  A persistent CTA resolves that look-back one tile late (after
+//      packing its next tile into a second window), when it no longer has to wait.
+// CTAs take tiles in increasing order: blockIdx.x when all tiles fit in one wave, else by ticket.
 #pragma once
 
 #include "common.cuh"
