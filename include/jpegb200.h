@@ -166,7 +166,11 @@ int          jpegb200_encoder_set_dct_mode(jpegb200_encoder *enc, int dct_mode);
 int          jpegb200_encoder_set_bytes_per_block(jpegb200_encoder *enc, int bytes_per_block);
 
 /* Description of one launch: `count` images of identical geometry, image i starting
- * at d_rgb + i*image_stride (top-down interleaved RGB, row pitch 3*width bytes). */
+ * at d_rgb + i*image_stride (top-down interleaved RGB, row pitch 3*width bytes).  No alignment
+ * is required of d_rgb, the stride or the width.  Pixel rows are fetched in whole 16-byte lines,
+ * so up to 15 bytes before the first and after the last pixel byte may be read (never used):
+ * they must be readable device memory, which holds for any pointer into a cudaMalloc'd (or
+ * pooled) allocation because allocations start and end on at least 256-byte boundaries. */
 typedef struct {
     const uint8_t *d_rgb;
     int32_t  width;
