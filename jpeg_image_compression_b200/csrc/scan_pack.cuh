@@ -266,7 +266,7 @@ k_scan_pack_stuff(const PackArgs a)
     uint32_t *s_sym = k2_smem_words + 2 * WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE;
     __shared__ uint32_t s_dc[16];
     __shared__ uint32_t s_strip_base[K2_WARPS];     // bit offset of each strip inside the tile
-    __shared__ uint32_t s_warp[K2_WARPS], s_carry, s_tile_bits;
+    __shared__ uint32_t s_warp[K2_WARPS], s_tile_bits;
     __shared__ uint64_t s_scratch[9];
     __shared__ __align__(8) uint64_t s_bar;         // completion of the symbol table's bulk copy
     __shared__ unsigned long long s_next_tile;
@@ -505,7 +505,6 @@ k_scan_pack_stuff(const PackArgs a)
             const uint64_t ff_excl = lookback_grouped(a.ff_agg + (uint64_t)img * a.tiles, ff_incl, tile, a.err, s_scratch);
             if (tid == 0) {
                 if (tile % LB_GROUP == LB_GROUP - 1) st_volatile_u64(ff_incl + tile / LB_GROUP, LB_VALID | (ff_excl + w.tile_ff));
-                s_carry = 0;
                 if (tile == a.tiles - 1) {
                     const uint64_t size = w.B1 - origin + ff_excl + w.tile_ff;
                     a.image_bytes[img] = size;
@@ -522,10 +521,13 @@ k_scan_pack_stuff(const PackArgs a)
             const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;
             uint8_t *out = a.out + (uint64_t)img * a.out_slot;
             const uint64_t out_base = (w.B0 - origin) + ff_excl;      // output index of window byte wb0
-            for (uint32_t i0 = wfirst; i0 < wlast; i0 += K2_THREADS) {
-                const uint32_t i = i0 + tid;
-                const uint32_t v = i < wlast ? masked_word(win, i, wb0, wb1) : 0u;
-                const uint32_t cnt = count_ff_bytes(v);
+            // two consecutive window words per thread and round: a typical tile (about 340 words) is one round
+            uint32_t carry = 0;                                       // stuffed zeros of the earlier rounds (uniform)
+            for (uint32_t i0 = wfirst; i0 < wlast; i0 += 2 * K2_THREADS) {
+                const uint32_t i = i0 + 2 * tid;
+                const uint32_t v0 = i < wlast ? masked_word(win, i, wb0, wb1) : 0u;
+                const uint32_t v1 = i + 1 < wlast ? masked_word(win, i + 1, wb0, wb1) : 0u;
+                const uint32_t cnt = count_ff_bytes(v0) + count_ff_bytes(v1);
                 uint32_t incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -534,7 +536,7 @@ k_scan_pack_stuff(const PackArgs a)
                 }
                 if (lane == 31) s_warp[warp] = incl;
                 __syncthreads();
-                uint32_t before = s_carry + incl - cnt;
+                uint32_t before = carry + incl - cnt;
                 uint32_t round_total = 0;
 #pragma unroll
                 for (int ww = 0; ww < K2_WARPS; ++ww) {
@@ -542,26 +544,30 @@ k_scan_pack_stuff(const PackArgs a)
                     if (ww < warp) before += ws;
                     round_total += ws;
                 }
+                carry += round_total;
                 if (i < wlast) {
-                    const uint32_t raw = win[i];
                     uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t wb = i * 4 + k;
-                        if (wb >= wb0 && wb < wb1) {
-                            const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
-                            if (pos < a.out_capacity) out[pos] = byte;
-                            ++pos;
-                            if (byte == 0xFF) {                         // huffman.c:29-31
-                                if (pos < a.out_capacity) out[pos] = 0x00;
-                                ++pos;
+                    for (int j = 0; j < 2; ++j) {
+                        if (i + j < wlast) {
+                            const uint32_t raw = win[i + j];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t wb = (i + j) * 4 + k;
+                                if (wb >= wb0 && wb < wb1) {
+                                    const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
+                                    if (pos < a.out_capacity) out[pos] = byte;
+                                    ++pos;
+                                    if (byte == 0xFF) {                 // huffman.c:29-31
+                                        if (pos < a.out_capacity) out[pos] = 0x00;
+                                        ++pos;
+                                    }
+                                }
                             }
                         }
                     }
                 }
-                __syncthreads();
-                if (tid == 0) s_carry += round_total;
-                __syncthreads();
+                __syncthreads();                                      // s_warp is rewritten in the next round
             }
             K2_TRACE(w.t, 7);
         }
