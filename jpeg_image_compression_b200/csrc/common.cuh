@@ -196,8 +196,9 @@ __device__ __forceinline__ uint64_t lookback_grouped(const uint64_t *agg, const 
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarp = nthreads >> 5;
     const int g0 = (tile / LB_GROUP) * LB_GROUP;
-    uint64_t sum = 0;
-    if (tid == 0 && g0 > 0) sum = lb_wait(incl + (tile / LB_GROUP) - 1, err);
+    uint32_t sum = 0;                      // aggregates of one group fit 32 bits; the checkpoint is added as 64 bits
+    uint64_t base = 0;
+    if (tid == 0 && g0 > 0) base = lb_wait(incl + (tile / LB_GROUP) - 1, err);
     constexpr int BATCH = 4;                 // 4 x 256 threads = one whole group per pass
     for (int j0 = g0 + tid; j0 < tile; j0 += nthreads * BATCH) {
         uint64_t v[BATCH];
@@ -210,15 +211,16 @@ __device__ __forceinline__ uint64_t lookback_grouped(const uint64_t *agg, const 
         for (int i = 0; i < BATCH; ++i) {
             const int j = j0 + i * nthreads;
             if (!(v[i] & LB_VALID)) v[i] = lb_wait(agg + j, err);
-            sum += v[i] & ~LB_VALID;
+            sum += (uint32_t)v[i];
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     __syncthreads();                       // s_scratch may still be read from a previous call
     if (lane == 0) s_scratch[warp] = sum;
+    if (tid == 0) s_scratch[8] = base;
     __syncthreads();
-    uint64_t excl = 0;
+    uint64_t excl = s_scratch[8];
     for (int w = 0; w < nwarp; ++w) excl += s_scratch[w];
     return excl;
 }

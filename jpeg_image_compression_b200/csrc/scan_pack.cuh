@@ -309,7 +309,8 @@ k_scan_pack_stuff(const PackArgs a)
         if (have_tile) {
             uint32_t *win = k2_smem_words + cur * WIN_WORDS;
             const uint32_t win_sa = smem_sa + (uint32_t)(cur * WIN_WORDS) * 4u;
-            const int img = (int)(t / (uint64_t)a.tiles), tile = (int)(t - (uint64_t)img * a.tiles);
+            const int img = a.count == 1 ? 0 : (int)((uint32_t)t / (uint32_t)a.tiles);   // tickets fit 32 bits
+            const int tile = (int)((uint32_t)t - (uint32_t)img * (uint32_t)a.tiles);
             const StripRec *recs = a.strips + (uint64_t)img * a.strips_avail;
             const uint32_t strip0 = (uint32_t)tile * K2_WARPS;
             const uint32_t nstrips = min((uint32_t)K2_WARPS, a.strips_owned - strip0);
@@ -342,7 +343,7 @@ k_scan_pack_stuff(const PackArgs a)
             // group's checkpoint.
             const uint32_t fix0 = c_dc_len[magnitude_class((int)recs[0].first_dc - (int)a.dc_pred0)];
             const int g0 = (tile / LB_GROUP) * LB_GROUP;
-            uint64_t part = 0;
+            uint32_t part = 0;                                       // a 1024-tile group holds < 2^29 bits
             {
                 const uint64_t base = (uint64_t)img * a.strips_avail;            // index of the image's strip 0
                 const uint32_t *sbits = a.strip_bits + base;
@@ -353,7 +354,7 @@ k_scan_pack_stuff(const PackArgs a)
                 const uint4 *v4 = reinterpret_cast<const uint4 *>(sbits + head);
                 for (uint32_t i = tid; i < nvec; i += K2_THREADS) {
                     const uint4 v = v4[i];
-                    part += (uint64_t)(v.x + v.y) + (uint64_t)(v.z + v.w);
+                    part += (v.x + v.y) + (v.z + v.w);
                 }
                 if (tail + tid < hi) part += sbits[tail + tid];
             }
@@ -381,7 +382,7 @@ k_scan_pack_stuff(const PackArgs a)
 
             K2_TRACE(t, 1);
             // ---- 1b. finish the tile bit offset ----------------------------------------------------------
-            if (tid == 0) part += g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
+            if (tid == 0) s_scratch[K2_WARPS] = g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (lane == 0) s_scratch[warp] = part;
@@ -398,7 +399,7 @@ k_scan_pack_stuff(const PackArgs a)
                 if (lane < K2_WARPS) s_strip_base[lane] = incl - tot;
             }
             __syncthreads();
-            uint64_t bit_excl = 0;
+            uint64_t bit_excl = s_scratch[K2_WARPS];                 // the group's checkpoint (64-bit)
 #pragma unroll
             for (int w = 0; w < K2_WARPS; ++w) bit_excl += s_scratch[w];
             const uint64_t begin = bit_excl + a.bit_phase, end = begin + s_tile_bits;
@@ -500,7 +501,8 @@ k_scan_pack_stuff(const PackArgs a)
         const PendingTile w = pend;
         if (w.t != ~0ull) {
             const uint32_t *win = k2_smem_words + (cur ^ 1) * WIN_WORDS;
-            const int img = (int)(w.t / (uint64_t)a.tiles), tile = (int)(w.t - (uint64_t)img * a.tiles);
+            const int img = a.count == 1 ? 0 : (int)((uint32_t)w.t / (uint32_t)a.tiles);
+            const int tile = (int)((uint32_t)w.t - (uint32_t)img * (uint32_t)a.tiles);
             uint64_t *ff_incl = a.ff_incl + (uint64_t)img * groups;
             const uint64_t ff_excl = lookback_grouped(a.ff_agg + (uint64_t)img * a.tiles, ff_incl, tile, a.err, s_scratch);
             if (tid == 0) {
