@@ -239,7 +239,8 @@ int jpegb200_encode_bmp_to_jpeg_host(jpegb200_encoder *enc, const uint8_t *bmp, 
 /* Tuning aid: with JPEGB200_K2_TRACE=1 in the environment K2 records 8 phase timestamps (ns) per
  * tile; this copies them out ([ntiles][8]). */
 int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t ntiles);
-/* Same for the block kernel (JPEGB200_K1_TRACE=1): 8 timestamps per persistent warp. */
+/* Same for the block kernel (JPEGB200_K1_TRACE=1): 8 timestamps per persistent warp, followed (pass
+ * 2 x the warp count) by the completion times of each warp's first 8 strips. */
 int jpegb200_encoder_read_k1_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t nwarps);
 
 /* ---- MCU-row stripes of one image across several GPUs ----------------------

@@ -45,9 +45,11 @@ constexpr int RAW_PITCH = 784;                       // 768 payload + 16 bytes o
 constexpr int RAW_BYTES = 8 * RAW_PITCH;             // 6272
 constexpr int Y_PITCH = 256;
 constexpr int Y_BYTES = 8 * Y_PITCH;                 // 2048
-constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES;    // 8320
+constexpr int ZZ_PITCH = 17;                          // words per lane: 16 coefficient words + 1 (bank-conflict-free)
+constexpr int ZZ_BYTES = 32 * ZZ_PITCH * 4;          // 2176
+constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES + ZZ_BYTES;    // 10496
 constexpr int ACLUT_BYTES = 16400;                   // 63 rows x 260 bytes + EOB length, then 16 DC lengths
-constexpr int K1_SMEM = ACLUT_BYTES + K1_WARPS * K1_WARP_SMEM;   // 82944
+constexpr int K1_SMEM = ACLUT_BYTES + K1_WARPS * K1_WARP_SMEM;   // 100368: two CTAs per SM
 
 // Everything a warp needs to know about one strip; computed once per strip (32-bit math).
 struct StripCtx {
@@ -222,6 +224,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *raw = smem + ACLUT_BYTES + warp * K1_WARP_SMEM;
     uint8_t *ybuf = raw + RAW_BYTES;
+    uint32_t *zs = reinterpret_cast<uint32_t *>(ybuf + Y_BYTES) + lane * ZZ_PITCH;   // this lane's 64 coefficient bytes
 
     K1_TRACE(0);
     // Static schedule: persistent warp i takes strips i, i + nwarps, ...; the 8 warps of a CTA work on 8
@@ -280,8 +283,9 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
 
         // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
         if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
-            // full strip, word-aligned rows: 3 LDS + DP4A/PRMT per 4 pixels, fully unrolled
-#pragma unroll
+            // full strip, word-aligned rows: 3 LDS + DP4A/PRMT per 4 pixels.  Two rows per trip, not fully
+            // unrolled: the kernel's hot loop has to stay inside the 32 KB instruction cache (L1.5)
+#pragma unroll 2
             for (int r = 0; r < 8; ++r) {
                 const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
                 uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
@@ -434,12 +438,20 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 K1_TRACE(4);
             }
             // AC bit cost: code length + amplitude bits per non-zero coefficient, ZRLs, EOB
-            uint32_t bits = 0, lastk = 0;                          // lastk = ACLUT_STRIDE * (index of the last non-zero)
+            // The walk is a real loop over bytes parked in shared memory, not 63 unrolled copies reading
+            // registers: the kernel's hot loop has to fit the SM's 32 KB instruction cache, otherwise the 16
+            // warps (each at its own place in the code) saturate the GPC-level instruction cache.
 #pragma unroll
+            for (int w = 0; w < 16; ++w) zs[w] = zw[w];
+            const uint8_t *zb = reinterpret_cast<const uint8_t *>(zs);
+            uint32_t bits = 0, lastk = 0;                          // lastk = ACLUT_STRIDE * (index of the last non-zero)
+            const uint8_t *lut = aclut;                            // row of zero run 0 for position k
+#pragma unroll 7
             for (int k = 1; k < 64; ++k) {
-                const uint32_t byte = __byte_perm(zw[k >> 2], 0u, 0x4440u + (uint32_t)(k & 3));
-                bits += aclut[byte + (uint32_t)((k - 1) * ACLUT_STRIDE) - lastk];
-                if (byte != 0) lastk = (uint32_t)(k * ACLUT_STRIDE);
+                const uint32_t byte = zb[k];
+                bits += lut[byte - lastk];
+                lut += ACLUT_STRIDE;
+                if (byte != 0) lastk = (uint32_t)(lut - aclut);   // = k * ACLUT_STRIDE
             }
             my_last = (lastk * 253u) >> 16;                        // lastk / 260 for lastk <= 63*260
             if (my_last != 63u) bits += aclut[ACLUT_ROWS * ACLUT_STRIDE];   // EOB code length (rle.c:121-123)
@@ -484,6 +496,13 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             }
         }
         __syncwarp();
+#ifdef JPEGB200_TRACE
+        // second half of the trace buffer: completion times of this warp's first 8 strips
+        if (trace && lane == 0) {
+            const uint32_t it = (s - (blockIdx.x * K1_WARPS + warp)) / nwarps;
+            if (it < 8) trace[(uint64_t)(nwarps + blockIdx.x * K1_WARPS + warp) * 8 + it] = globaltimer_ns();
+        }
+#endif
     }
 
     K1_TRACE(6);

@@ -350,8 +350,8 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
     int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
     if (const char *e = getenv("JPEGB200_K1_GRID")) grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, atoi(e)));   // tuning aid
     if (getenv("JPEGB200_K1_TRACE")) {              // tuning aid: per-warp timestamps
-        if (int rc = enc->trace1.reserve((uint64_t)grid * K1_WARPS * 64)) return rc;
-        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * K1_WARPS * 64, st));
+        if (int rc = enc->trace1.reserve((uint64_t)grid * K1_WARPS * 128)) return rc;     // [warps][8] phases, [warps][8] strip ends
+        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * K1_WARPS * 128, st));
     }
     {
         TimedLaunch t(enc, st, KID_BLOCK);

@@ -18,9 +18,10 @@ torch.cuda.synchronize()
 print("kernel times (events):", enc.kernel_times())
 strips = ((w + 255) // 256) * ((h + 7) // 8)
 nwarps = min((strips + 7) // 8, 296) * 8
-tr = np.zeros((nwarps, 8), np.uint64)
-check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, nwarps), "trace")
-t = tr.astype(np.int64)
+tr = np.zeros((2 * nwarps, 8), np.uint64)
+check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, 2 * nwarps), "trace")
+t = tr[:nwarps].astype(np.int64)
+ends = tr[nwarps:].astype(np.int64)
 t0 = t[:, 0].min()
 names = ["entry", "prologue", "tile0", "pre-table", "table", "strip0-late", "exit"]
 print("warps", nwarps, "strips", strips, "span us", (t[:, 6].max() - t0) / 1e3)
@@ -42,3 +43,12 @@ for name, grp in (("two-strip", two_), ("one-strip", ~two_)):
 two = np.arange(nwarps) + nwarps < strips
 life = (t[:, 6] - t[:, 0]) / 1e3
 print(f"warp life: two-strip warps median {np.median(life[two]):.2f}  one-strip warps median {np.median(life[~two]) if (~two).any() else 0:.2f}")
+prev = t[:, 2]                                   # arrival of the first tile
+for it in range(8):
+    col = ends[:, it]
+    okk = col > 0
+    if not okk.any():
+        break
+    dur = (col[okk] - prev[okk]) / 1e3
+    print(f"strip {it}: n={okk.sum():5d} duration median {np.median(dur):5.2f} p90 {np.percentile(dur, 90):5.2f} max {dur.max():5.2f}  (ends at median {np.median((col[okk] - t0) / 1e3):6.2f})")
+    prev = col
