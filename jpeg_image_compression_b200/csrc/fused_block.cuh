@@ -203,6 +203,74 @@ __device__ __forceinline__ void dct8(float &x0, float &x1, float &x2, float &x3,
     x7 = fmaf(b3, -C1, fmaf(b2, C3, fmaf(b1, -C5, b0 * C7)));
 }
 
+// ---- the same butterfly on two columns at once (Blackwell packed fp32: FADD2 / FMUL2 / FFMA2) ----------
+// Element for element the operation sequence of dct8 (fma.rn.f32x2 etc. round each half like the scalar
+// instruction), so the guard-band analysis is unchanged; it halves the instruction count of the column
+// pass.  A pair lives in an aligned register pair, packing and unpacking are free.  The constants
+// come from constant memory (ptxas keeps them in uniform registers).
+typedef unsigned long long f32x2;
+__constant__ float2 c_dct2[9] = {
+    {0.98078528040323044913f, 0.98078528040323044913f},   // 0: C1
+    {0.83146961230254523708f, 0.83146961230254523708f},   // 1: C3
+    {0.55557023301960222474f, 0.55557023301960222474f},   // 2: C5
+    {0.19509032201612826785f, 0.19509032201612826785f},   // 3: C7
+    {0.41421356237309504880f, 0.41421356237309504880f},   // 4: tan(pi/8)
+    {-0.98078528040323044913f, -0.98078528040323044913f}, // 5: -C1
+    {-0.55557023301960222474f, -0.55557023301960222474f}, // 6: -C5
+    {-0.19509032201612826785f, -0.19509032201612826785f}, // 7: -C7
+    {-8388736.0f, -8388736.0f}};                           // 8: -(2^23 + 128), see u8_to_centered
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi));
+    return p;
+}
+__device__ __forceinline__ void unpack2(f32x2 p, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 kdct2(int i) { return *reinterpret_cast<const f32x2 *>(&c_dct2[i]); }
+
+__device__ __forceinline__ void dct8_2(f32x2 &x0, f32x2 &x1, f32x2 &x2, f32x2 &x3, f32x2 &x4, f32x2 &x5, f32x2 &x6,
+                                       f32x2 &x7)
+{
+    const f32x2 C1 = kdct2(0), C3 = kdct2(1), C5 = kdct2(2), C7 = kdct2(3), TAN = kdct2(4);
+    const f32x2 NC1 = kdct2(5), NC5 = kdct2(6), NC7 = kdct2(7);
+    const f32x2 a0 = add2(x0, x7), a1 = add2(x1, x6), a2 = add2(x2, x5), a3 = add2(x3, x4);
+    const f32x2 b0 = sub2(x0, x7), b1 = sub2(x1, x6), b2 = sub2(x2, x5), b3 = sub2(x3, x4);
+    const f32x2 e0 = add2(a0, a3), e1 = add2(a1, a2), d0 = sub2(a0, a3), d1 = sub2(a1, a2);
+    const f32x2 nd1 = sub2(a2, a1);                               // -d1, exactly
+    x0 = add2(e0, e1);
+    x4 = sub2(e0, e1);
+    x2 = fma2(d1, TAN, d0);
+    x6 = fma2(d0, TAN, nd1);
+    x1 = fma2(b3, C7, fma2(b2, C5, fma2(b1, C3, mul2(b0, C1))));
+    x3 = fma2(b3, NC5, fma2(b2, NC1, fma2(b1, NC7, mul2(b0, C3))));
+    x5 = fma2(b3, C3, fma2(b2, C7, fma2(b1, NC1, mul2(b0, C5))));
+    x7 = fma2(b3, NC1, fma2(b2, C3, fma2(b1, NC5, mul2(b0, C7))));
+}
+
 // scale class of a frequency index: 0 -> g=1, 1 -> g=cos(pi/8), 2 -> g=cos(pi/4)
 __host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 : (k == 4 ? 2 : 0); }
 
@@ -339,16 +407,29 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 const uint2 v = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
                 absdev = __vsadu4(v.x, 0x80808080u) + absdev;
                 absdev = __vsadu4(v.y, 0x80808080u) + absdev;
+                // u8 -> centred f32 (converter.c:84): byte into the mantissa of 2^23, then one packed subtraction
+                // per two pixels (0x4B0000xx is 2^23 + xx; subtracting 2^23 + 128 is exact)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    x[r][c] = u8_to_centered(v.x, c);
-                    x[r][c + 4] = u8_to_centered(v.y, c);
+                for (int c = 0; c < 4; c += 2) {
+                    const f32x2 lo = pack2(__uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7650u + c)),
+                                           __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7651u + c)));
+                    const f32x2 hi = pack2(__uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7650u + c)),
+                                           __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7651u + c)));
+                    unpack2(add2(lo, kdct2(8)), x[r][c], x[r][c + 1]);
+                    unpack2(add2(hi, kdct2(8)), x[r][c + 4], x[r][c + 5]);
                 }
-                dct8(x[r][0], x[r][1], x[r][2], x[r][3], x[r][4], x[r][5], x[r][6], x[r][7]);
+                dct8(x[r][0], x[r][1], x[r][2], x[r][3], x[r][4], x[r][5], x[r][6], x[r][7]);   // along the row
             }
+            // down the columns, two adjacent columns per instruction
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                dct8(x[0][c], x[1][c], x[2][c], x[3][c], x[4][c], x[5][c], x[6][c], x[7][c]);
+            for (int c = 0; c < 8; c += 2) {
+                f32x2 p[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) p[r] = pack2(x[r][c], x[r][c + 1]);
+                dct8_2(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) unpack2(p[r], x[r][c], x[r][c + 1]);
+            }
 
             // Ac = sum |Y - m|, m = the block's rounded mean luma (from the exact DC sum)
             uint32_t absmean = 0;
