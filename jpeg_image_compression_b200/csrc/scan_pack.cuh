@@ -268,6 +268,7 @@ k_scan_pack_stuff(const PackArgs a)
     __shared__ uint32_t s_strip_base[K2_WARPS];     // bit offset of each strip inside the tile
     __shared__ uint32_t s_warp[K2_WARPS], s_tile_bits;
     __shared__ uint64_t s_scratch[9];
+    __shared__ uint32_t s_halo[20];                 // the block after the tile: 16 coefficient words, blkinfo, non-zero map (2), predictor
     __shared__ __align__(8) uint64_t s_bar;         // completion of the symbol table's bulk copy
     __shared__ unsigned long long s_next_tile;
 
@@ -277,6 +278,7 @@ k_scan_pack_stuff(const PackArgs a)
     const uint32_t stage_sa = smem_sa + (uint32_t)(2 * WIN_WORDS + tid * K2_STAGE_STRIDE) * 4u;
     const uint32_t sym_sa = smem_sa + (uint32_t)(2 * WIN_WORDS + K2_THREADS * K2_STAGE_STRIDE) * 4u;
     const uint32_t dc_sa = smem_u32(s_dc);
+    const uint32_t halo_sa = smem_u32(s_halo);
     if (tid == 0) {
         s_next_tile = a.dynamic_tiles ? atomicAdd(a.tile_counter, 1ull) : (unsigned long long)blockIdx.x;
         mbar_init(&s_bar, 1);
@@ -335,6 +337,14 @@ k_scan_pack_stuff(const PackArgs a)
             }
             int prev_dc = 0;
             if (have && lane == 0) prev_dc = my_strip == 0 ? (int)a.dc_pred0 : (int)recs[my_strip - 1].last_dc;
+            // the block that follows the tile in raster order (step 3 needs its first few bits): the last warp
+            // requests its 16 coefficient words and its blkinfo now, together with everything else
+            uint32_t halo_word = 0;
+            if (warp == K2_WARPS - 1 && lane < 17 && strip0 + nstrips < a.strips_avail) {
+                const uint32_t hst = strip0 + nstrips, hbrow = hst / a.spr, hsx = hst - hbrow * a.spr;
+                const uint64_t hb = img_block0 + (uint64_t)hbrow * a.bw + hsx * 32u;
+                halo_word = lane < 16 ? reinterpret_cast<const uint32_t *>(a.coef + hb * 64)[lane] : a.blkinfo[hb];
+            }
 
             // ---- 1a. tile bit offset, wait-free: the loads go out together with the coefficient loads -----
             // K1 left complete per-strip bit counts (only the image's very first DC symbol is missing: its
@@ -359,7 +369,11 @@ k_scan_pack_stuff(const PackArgs a)
                 if (tail + tid < hi) part += sbits[tail + tid];
             }
             uint32_t tile_tot = 0;                                   // warp 0: this lane's strip of the tile
-            if (warp == 0 && (uint32_t)lane < nstrips) tile_tot = recs[strip0 + lane].bits;
+            if (warp == 0 && (uint32_t)lane < nstrips) {
+                const StripRec rec = recs[strip0 + lane];
+                tile_tot = rec.bits;
+                if ((uint32_t)lane == nstrips - 1) s_halo[19] = (uint32_t)(int)rec.last_dc;   // predictor of the successor block
+            }
 
             if (have) {
 #pragma unroll
@@ -372,6 +386,14 @@ k_scan_pack_stuff(const PackArgs a)
                 }
                 mlo &= ~1u;                                          // position 0 is the DC
                 my_dc = (int)(int8_t)(q[0].x & 0xFFu);
+            }
+            if (warp == K2_WARPS - 1) {                              // park the successor block and its non-zero map
+                const uint32_t nib = lane < 16 ? nonzero_nibble(halo_word) : 0u;
+                const uint32_t hlo = __reduce_or_sync(0xffffffffu, lane < 8 ? nib << (4 * lane) : 0u) & ~1u;
+                const uint32_t hhi = __reduce_or_sync(0xffffffffu, lane >= 8 ? nib << (4 * (lane & 7)) : 0u);
+                if (lane < 17) s_halo[lane] = halo_word;
+                if (lane == 17) s_halo[17] = hlo;
+                if (lane == 18) s_halo[18] = hhi;
             }
             // predictor: previous block in raster order (rle.c:59-70) = the previous lane's block, or the
             // previous strip's last block for lane 0 (fetched above)
@@ -442,30 +464,37 @@ k_scan_pack_stuff(const PackArgs a)
                 uint32_t pos = (uint32_t)(end - (w0 << 5));
                 const uint32_t lim = (uint32_t)(limit - (w0 << 5));
                 uint32_t st = strip0 + nstrips;                      // raster successor of the tile's last block
-                int hprev = (int)recs[st - 1].last_dc;
-                uint32_t lb = 0;
-                for (int n = 0; n < 2 && pos < lim && st < a.strips_avail; ++n) {
-                    const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
-                    const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
-                    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
-                    uint32_t hlo = 0, hhi = 0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t q = src[i];
-                        stage[i] = q;
-                        if (i < 8) hlo |= nonzero_nibble(q) << (4 * i);
-                        else hhi |= nonzero_nibble(q) << (4 * (i - 8));
-                    }
-                    hlo &= ~1u;
-                    const int hdc = (int)(int8_t)(src[0] & 0xFFu);
-                    const uint32_t hinfo = a.blkinfo[b];
-                    encode_block(stage_sa, hdc, hprev, (int)((hinfo >> 16) & 63u), hlo, hhi, sym_sa, dc_sa,
-                                 [&](uint32_t v, uint32_t nb) {
-                                     put_clipped(win_sa, pos, lim, v, nb);
-                                     return pos < lim;
-                                 });
+                int hprev = (int)s_halo[19];
+                auto emit_clipped = [&](uint32_t v, uint32_t nb) {
+                    put_clipped(win_sa, pos, lim, v, nb);
+                    return pos < lim;
+                };
+                if (st < a.strips_avail) {
+                    // the first successor block was staged in s_halo during step 0
+                    const int hdc = (int)(int8_t)(s_halo[0] & 0xFFu);
+                    encode_block(halo_sa, hdc, hprev, (int)((s_halo[16] >> 16) & 63u), s_halo[17], s_halo[18], sym_sa, dc_sa,
+                                 emit_clipped);
                     hprev = hdc;
-                    if (++lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
+                    uint32_t lb = 1;
+                    if (lb >= strip_blocks(st, a.spr, a.bw)) { lb = 0; ++st; }
+                    // rare: that block was shorter than the missing bits (a block can be as short as 6 bits)
+                    if (pos < lim && st < a.strips_avail) {
+                        const uint32_t brow = st / a.spr, sx = st - brow * a.spr;
+                        const uint64_t b = img_block0 + (uint64_t)brow * a.bw + sx * 32u + lb;
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.coef + b * 64);
+                        uint32_t hlo = 0, hhi = 0;
+#pragma unroll 1
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t q = src[i];
+                            stage[i] = q;
+                            if (i < 8) hlo |= nonzero_nibble(q) << (4 * i);
+                            else hhi |= nonzero_nibble(q) << (4 * (i - 8));
+                        }
+                        hlo &= ~1u;
+                        const uint32_t hinfo = a.blkinfo[b];
+                        encode_block(stage_sa, (int)(int8_t)(src[0] & 0xFFu), hprev, (int)((hinfo >> 16) & 63u), hlo, hhi, sym_sa,
+                                     dc_sa, emit_clipped);
+                    }
                 }
             }
             __syncthreads();
