@@ -527,7 +527,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             const uint8_t *zb = reinterpret_cast<const uint8_t *>(zs);
             uint32_t bits = 0, lastk = 0;                          // lastk = ACLUT_STRIDE * (index of the last non-zero)
             const uint8_t *lut = aclut;                            // row of zero run 0 for position k
-#pragma unroll 7
+#pragma unroll 21                     // 3 trips: measured best between code size (instruction cache) and loop overhead
             for (int k = 1; k < 64; ++k) {
                 const uint32_t byte = zb[k];
                 bits += lut[byte - lastk];
