@@ -52,6 +52,8 @@ struct Geom {
     int count;
     uint64_t blocks_per_image;
     uint64_t total_strips;
+    int use_tmap;            // 1: pixel tiles are fetched with one tensor-map TMA copy per strip (16-byte aligned
+                             // base / pitch / stride); 0: one bulk copy per pixel row (any alignment)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -93,6 +95,15 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// one box of a 3-D tensor map (x: 32-bit words in a row, y: pixel rows, z: images) -> shared memory (128-byte aligned)
+__device__ __forceinline__ void tensor_g2s_3d(void *smem_dst, const void *tmap, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {

@@ -33,6 +33,8 @@
 // formulations and is quantized with the reference's own operation sequence.
 #pragma once
 
+#include <cuda.h>          // CUtensorMap (type only; the encoder function is looked up at run time)
+
 #include "common.cuh"
 #include "scan_pack.cuh"
 
@@ -49,7 +51,9 @@ constexpr int ZZ_PITCH = 17;                          // words per lane: 16 coef
 constexpr int ZZ_BYTES = 32 * ZZ_PITCH * 4;          // 2176
 constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES + ZZ_BYTES;    // 10496
 constexpr int ACLUT_BYTES = 16400;                   // 63 rows x 260 bytes + EOB length, then 16 DC lengths
-constexpr int K1_SMEM = ACLUT_BYTES + K1_WARPS * K1_WARP_SMEM;   // 100368: two CTAs per SM
+constexpr int K1_TABLE_BYTES = 16512;                // table area rounded up to 128 bytes: tensor-map copies need that alignment
+constexpr int K1_SMEM = K1_TABLE_BYTES + K1_WARPS * K1_WARP_SMEM;   // 100480: two CTAs per SM
+constexpr int TMAP_ROW_BYTES = 768;                  // a tensor-map box is dense: 8 rows x 768 bytes
 
 // Everything a warp needs to know about one strip; computed once per strip (32-bit math).
 struct StripCtx {
@@ -60,6 +64,7 @@ struct StripCtx {
     int npx;                 // real pixels per row in the strip (<= 256)
     int vb;                  // 8x8 blocks in the strip (<= 32)
     uint32_t mispack;        // 16-byte phase of each of the 8 row pointers, 4 bits per row
+    int tx, ty, tz;          // tensor-map coordinates of the tile: word column, pixel row, image
     // the block that precedes the strip in raster order (its DC is the strip's first predictor)
     const uint8_t *halo;     // its top-left pixel; nullptr for the first strip of an image
     int halo_rmax, halo_cmax;// last real row / column inside that block (edges replicate)
@@ -107,6 +112,9 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
     c.npx = min(256, g.w - (int)(sx * 256u));
     c.vb = min(32, g.bw - (int)(sx * 32u));
     c.mispack = 0;                                  // filled in by strip_issue_loads
+    c.tx = (int)(sx * 192u);
+    c.ty = (int)(brow * 8u);
+    c.tz = (int)img;
     if (sx > 0) {                                   // previous block is in the same block row
         c.halo = c.row0 - 24;
         c.halo_rmax = c.rmax;
@@ -127,8 +135,19 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
 // row r, all completed through the warp's mbarrier.  Each copy starts at the row's 16-byte-aligned
 // address and covers whole 16-byte chunks, so any width / base alignment works.  Also records the
 // rows' 16-byte phases in c.mispack.  Must be called by the whole warp.
-__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane)
+__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane, const CUtensorMap *tmap)
 {
+    if (tmap) {
+        // aligned input: ONE tensor-map copy of the 8 x 768-byte box (rows and columns beyond the image are
+        // zero-filled and never used: the luma pass clamps the row and stops at the last real pixel)
+        c.mispack = 0;
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, 8 * TMAP_ROW_BYTES);
+            tensor_g2s_3d(raw, tmap, c.tx, c.ty, c.tz, bar);
+        }
+        return;
+    }
     const int r = lane & 7;
     const uint8_t *row = c.row0 + (int64_t)min(r, c.rmax) * c.pitch;
     const uint32_t mis = (uint32_t)(uintptr_t)row & 15u;
@@ -279,18 +298,20 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                StripRec *__restrict__ strips, uint32_t *__restrict__ strip_bits, const uint8_t *__restrict__ tables,
                unsigned long long *__restrict__ flagged_counter, const int exact_mode,
                uint64_t *__restrict__ lookback_state, const uint64_t lookback_words,
-               unsigned long long *__restrict__ trace)
+               unsigned long long *__restrict__ trace, const __grid_constant__ CUtensorMap tmap_param)
 {
 #ifdef JPEGB200_TRACE   // tracing build only (make trace -> libjpegb200_trace.so)
 #define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * K1_WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
 #else
 #define K1_TRACE(slot) do { } while (0)
 #endif
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *aclut = smem;
     const uint8_t *s_dclen = smem + TBL_DC_LEN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *raw = smem + ACLUT_BYTES + warp * K1_WARP_SMEM;
+    uint8_t *raw = smem + K1_TABLE_BYTES + warp * K1_WARP_SMEM;
+    const CUtensorMap *tmap = g.use_tmap ? &tmap_param : nullptr;
+    const uint32_t raw_pitch = g.use_tmap ? TMAP_ROW_BYTES : RAW_PITCH;
     uint8_t *ybuf = raw + RAW_BYTES;
     uint32_t *zs = reinterpret_cast<uint32_t *>(ybuf + Y_BYTES) + lane * ZZ_PITCH;   // this lane's 64 coefficient bytes
 
@@ -316,7 +337,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     if (s < total) {
         pos = strip_pos(g, s);
         cur = strip_ctx(g, pos);
-        strip_issue_loads(cur, raw, bar, lane);                  // first strip's pixels are in flight ...
+        strip_issue_loads(cur, raw, bar, lane, tmap);                  // first strip's pixels are in flight ...
     }
     if (threadIdx.x == 0) {                                      // ... while the bit-cost table is staged (one 16 KB bulk copy)
         mbar_expect_tx(&s_bar[K1_WARPS], ACLUT_BYTES);
@@ -355,7 +376,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
             // unrolled: the kernel's hot loop has to stay inside the 32 KB instruction cache (L1.5)
 #pragma unroll 2
             for (int r = 0; r < 8; ++r) {
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
                 uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
                 yo[lane] = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi);
                 yo[lane + 32] = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
@@ -368,7 +389,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 const int r = item >> 6, gc = item & 63;
                 if (gc < ngroups) {
                     const uint32_t mis = (cur.mispack >> (4 * r)) & 15u;
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + r * RAW_PITCH) + (mis >> 2) + 3 * gc;
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch) + (mis >> 2) + 3 * gc;
                     const uint32_t sh = (mis & 3u) * 8u;
                     const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
                     reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] =
@@ -383,7 +404,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         if (s + nwarps < total) {
             strip_advance(g, pos, dq, dr);
             cur = strip_ctx(g, pos);
-            strip_issue_loads(cur, raw, bar, lane);
+            strip_issue_loads(cur, raw, bar, lane, tmap);
         }
 
         // right-edge replication inside the last real block (converter.c:36)

@@ -342,10 +342,49 @@ struct TimedLaunch {
     ~TimedLaunch() { if (stop) cudaEventRecord(stop, st); }
 };
 
+// cuTensorMapEncodeTiled, looked up through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+        if (getenv("JPEGB200_NO_TMAP")) return nullptr;          // tuning aid: force the per-row copies
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// Describe the pixel array as a 3-D tensor of 32-bit words (words per row, rows, images) so that K1 can fetch a
+// strip's 8 x 768-byte tile with one TMA copy.  Needs 16-byte aligned base, pitch and image stride and top-down
+// rows; otherwise (or without the driver entry point) K1 falls back to one bulk copy per pixel row.
+static bool make_tensor_map(const Geom &g, CUtensorMap *tm)
+{
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc || g.row_pitch <= 0 || (g.row_pitch & 15) || ((uintptr_t)g.rgb & 15) || (g.count > 1 && (g.image_stride & 15)))
+        return false;
+    if ((uint64_t)g.row_pitch * (uint64_t)g.h > g.image_stride && g.count > 1) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(g.row_pitch / 4), (cuuint64_t)g.h, (cuuint64_t)g.count};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.row_pitch, g.count > 1 ? (cuuint64_t)g.image_stride : (cuuint64_t)g.row_pitch * (cuuint64_t)g.h};
+    const cuuint32_t box[3] = {TMAP_ROW_BYTES / 4, 8, 1}, estr[3] = {1, 1, 1};
+    if (strides[1] & 15) return false;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(g.rgb), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // K1: fused block kernel, persistent, K1_CTAS_PER_SM CTAs per SM
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
 {
-    const Geom &g = enc->geom;
+    Geom &g = enc->geom;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    g.use_tmap = make_tensor_map(g, &tmap) ? 1 : 0;
     const uint64_t want = (g.total_strips + K1_WARPS - 1) / K1_WARPS;
     int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
     if (const char *e = getenv("JPEGB200_K1_GRID")) grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, atoi(e)));   // tuning aid
@@ -361,7 +400,7 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
                                                            static_cast<uint32_t *>(enc->strip_bits.ptr),
                                                            static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc),
                                                            enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
-                                                           enc->lookback_words, static_cast<unsigned long long *>(enc->trace1.ptr));
+                                                           enc->lookback_words, static_cast<unsigned long long *>(enc->trace1.ptr), tmap);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;

@@ -489,3 +489,18 @@ def test_gigapixel_equals_streaming_oracle(enc, oracle):
     want = oracle.encode_scan_synth_banded(w, h, 1, 20, 8, 0)
     assert n == len(want)
     assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+
+
+def test_tensor_map_path_edges(enc, oracle):
+    """Inputs with a 16-byte aligned base and pitch take K1's tensor-map TMA path (one copy per 8 x 768-byte
+    tile): ragged heights (zero-filled rows below the image must not leak: the luma pass clamps the row),
+    a partial last strip in each block row, single-strip and many-strip widths, and a batch of them."""
+    for (w, h) in ((320, 13), (320, 77), (256, 7), (1024, 61), (16, 9), (2048, 23), (3072, 8)):
+        assert (3 * w) % 16 == 0
+        rgb = oracle.synth_rgb(w, h, 5, 40)
+        assert enc.encode(rgb) == oracle.encode_scan(rgb), (w, h)
+    rng = np.random.default_rng(11)
+    imgs = rng.integers(0, 256, (6, 21, 336, 3), dtype=np.uint8)          # stride 21168 = 16 * 1323
+    scans = enc.encode_batch(imgs)
+    for i in range(6):
+        assert scans[i] == oracle.encode_scan(imgs[i]), i
