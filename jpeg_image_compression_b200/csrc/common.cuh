@@ -65,6 +65,16 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
 }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)      // both 8-byte aligned
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// the executing thread arrives on the mbarrier once all its earlier cp.async copies have landed (the
+// barrier's arrival count has to include these arrivals)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 

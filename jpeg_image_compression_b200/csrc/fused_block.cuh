@@ -49,10 +49,11 @@ constexpr int Y_PITCH = 256;
 constexpr int Y_BYTES = 8 * Y_PITCH;                 // 2048
 constexpr int ZZ_PITCH = 17;                          // words per lane: 16 coefficient words + 1 (bank-conflict-free)
 constexpr int ZZ_BYTES = 32 * ZZ_PITCH * 4;          // 2176
-constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES + ZZ_BYTES;    // 10496
+constexpr int HALO_BYTES = 256;                      // the raster-predecessor block's 8 x 24 RGB bytes (192), padded
+constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES + ZZ_BYTES + HALO_BYTES;    // 10752 = 84 x 128
 constexpr int ACLUT_BYTES = 16400;                   // 63 rows x 260 bytes + EOB length, then 16 DC lengths
 constexpr int K1_TABLE_BYTES = 16512;                // table area rounded up to 128 bytes: tensor-map copies need that alignment
-constexpr int K1_SMEM = K1_TABLE_BYTES + K1_WARPS * K1_WARP_SMEM;   // 100480: two CTAs per SM
+constexpr int K1_SMEM = K1_TABLE_BYTES + K1_WARPS * K1_WARP_SMEM;   // 102528: two CTAs per SM
 constexpr int TMAP_ROW_BYTES = 768;                  // a tensor-map box is dense: 8 rows x 768 bytes
 
 // Everything a warp needs to know about one strip; computed once per strip (32-bit math).
@@ -135,7 +136,8 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
 // row r, all completed through the warp's mbarrier.  Each copy starts at the row's 16-byte-aligned
 // address and covers whole 16-byte chunks, so any width / base alignment works.  Also records the
 // rows' 16-byte phases in c.mispack.  Must be called by the whole warp.
-__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane, const CUtensorMap *tmap)
+__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint8_t *hal, uint64_t *bar, int lane,
+                                                  const CUtensorMap *tmap)
 {
     if (tmap) {
         // aligned input: ONE tensor-map copy of the 8 x 768-byte box (rows and columns beyond the image are
@@ -146,6 +148,13 @@ __device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uin
             mbar_expect_tx(bar, 8 * TMAP_ROW_BYTES);
             tensor_g2s_3d(raw, tmap, c.tx, c.ty, c.tz, bar);
         }
+        // the raster-predecessor block (8 rows x 24 bytes, 8-byte aligned here) rides along as 24 asynchronous
+        // 8-byte copies whose completion is folded into the same mbarrier phase (every lane arrives once)
+        if (c.halo != nullptr && lane < 24) {
+            const int r = lane / 3, part = lane - 3 * r;
+            cp_async8(hal + lane * 8, c.halo + (int64_t)min(r, c.halo_rmax) * c.pitch + 8 * part);
+        }
+        cp_async_mbar_arrive_noinc(bar);
         return;
     }
     const int r = lane & 7;
@@ -314,6 +323,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     const uint32_t raw_pitch = g.use_tmap ? TMAP_ROW_BYTES : RAW_PITCH;
     uint8_t *ybuf = raw + RAW_BYTES;
     uint32_t *zs = reinterpret_cast<uint32_t *>(ybuf + Y_BYTES) + lane * ZZ_PITCH;   // this lane's 64 coefficient bytes
+    uint8_t *hal = ybuf + Y_BYTES + ZZ_BYTES;                    // predecessor block, tensor-map path only
 
     K1_TRACE(0);
     // Static schedule: persistent warp i takes strips i, i + nwarps, ...; the 8 warps of a CTA work on 8
@@ -326,7 +336,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     uint32_t s = blockIdx.x * K1_WARPS + warp;
     __shared__ __align__(8) uint64_t s_bar[K1_WARPS + 1];      // one mbarrier per warp (pixel tiles) + one for the table
     uint64_t *bar = &s_bar[warp];
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0) mbar_init(bar, g.use_tmap ? 33 : 1);          // tensor-map path: + one asynchronous arrival per lane
     if (threadIdx.x == 0) mbar_init(&s_bar[K1_WARPS], 1);
     mbar_fence_init();
     __syncthreads();
@@ -337,7 +347,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
     if (s < total) {
         pos = strip_pos(g, s);
         cur = strip_ctx(g, pos);
-        strip_issue_loads(cur, raw, bar, lane, tmap);                  // first strip's pixels are in flight ...
+        strip_issue_loads(cur, raw, hal, bar, lane, tmap);                  // first strip's pixels are in flight ...
     }
     if (threadIdx.x == 0) {                                      // ... while the bit-cost table is staged (one 16 KB bulk copy)
         mbar_expect_tx(&s_bar[K1_WARPS], ACLUT_BYTES);
@@ -360,7 +370,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         // luma sum of the raster-predecessor block: lane l covers row l/4, columns 2*(l%4) and +1;
         // the loads are issued now and consumed after the transform
         uint32_t halo_y = 0;
-        if (cur.halo) {
+        if (cur.halo && !tmap) {
             const uint8_t *hp = cur.halo + (int64_t)min(lane >> 2, cur.halo_rmax) * cur.pitch;
             const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
             const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
@@ -368,6 +378,12 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
+        if (cur.halo && tmap) {                          // same sum from the block staged in shared memory
+            const uint8_t *hp = hal + 24 * (lane >> 2);
+            const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
+            const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
+            halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
+        }
         if (!table_ready) K1_TRACE(2);
 
         // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
@@ -404,7 +420,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
         if (s + nwarps < total) {
             strip_advance(g, pos, dq, dr);
             cur = strip_ctx(g, pos);
-            strip_issue_loads(cur, raw, bar, lane, tmap);
+            strip_issue_loads(cur, raw, hal, bar, lane, tmap);
         }
 
         // right-edge replication inside the last real block (converter.c:36)
