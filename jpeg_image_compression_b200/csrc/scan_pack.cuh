@@ -546,7 +546,6 @@ k_scan_pack_stuff(const PackArgs a)
                     if (size > a.out_capacity) atomicOr(a.err, a.count == 1 ? ERRBIT_OUTPUT : ERRBIT_WORKSPACE);
                 }
             }
-            __syncthreads();
             K2_TRACE(w.t, 6);
             const uint32_t wb0 = (uint32_t)(w.B0 - 4 * w.w0), wb1 = (uint32_t)(w.B1 - 4 * w.w0);
             const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;
@@ -555,6 +554,7 @@ k_scan_pack_stuff(const PackArgs a)
             // two consecutive window words per thread and round: a typical tile (about 340 words) is one round
             uint32_t carry = 0;                                       // stuffed zeros of the earlier rounds (uniform)
             for (uint32_t i0 = wfirst; i0 < wlast; i0 += 2 * K2_THREADS) {
+                if (i0 != wfirst) __syncthreads();                    // s_warp is rewritten in every round
                 const uint32_t i = i0 + 2 * tid;
                 const uint32_t v0 = i < wlast ? masked_word(win, i, wb0, wb1) : 0u;
                 const uint32_t v1 = i + 1 < wlast ? masked_word(win, i + 1, wb0, wb1) : 0u;
@@ -598,7 +598,6 @@ k_scan_pack_stuff(const PackArgs a)
                         }
                     }
                 }
-                __syncthreads();                                      // s_warp is rewritten in the next round
             }
             K2_TRACE(w.t, 7);
         }
