@@ -464,8 +464,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20000 for uhd4k, 200 for batch1080p, 100 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default: 200 / 5 / 5)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uhd4k", choices=["uhd4k", "batch1080p"])
     ap.add_argument("--batch", type=int, default=512, help="images per step per GPU for batch1080p")
@@ -474,13 +474,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sensitivity", action="store_true", help="skip the amp=0 / amp=64 rows")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        dsteps, dwarm = 100, 5                              # the CPU arm: about a minute
+    elif args.workload == "batch1080p":
+        dsteps, dwarm = 200, 5
+    else:
+        dsteps, dwarm = 20000, 200                          # 0.5 s timed region at 4K
+    args.steps = dsteps if args.steps is None else args.steps
+    args.warmup = max(dwarm if args.warmup is None else args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if args.steps == 2000 and args.warmup == 200:      # defaults: keep the CPU arm to about a minute
-            args.steps, args.warmup = 100, 5
         run_reference(args, rank, world)
         return
     run_ours(args, rank, local_rank, world)
