@@ -61,10 +61,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
-}
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)      // both 8-byte aligned
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -75,8 +71,6 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ---- TMA bulk copies (cp.async.bulk -> UBLKCP) completed through an mbarrier ------------------
 // nanosecond wall clock shared by all SMs (tuning aids only)
