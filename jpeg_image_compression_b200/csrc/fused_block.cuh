@@ -7,17 +7,19 @@
 //
 // Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels,
 // 6 KB of RGB).  One warp owns a strip:
-//   1. TMA bulk copies (cp.async.bulk / UBLKCP, one per pixel row, mbarrier-completed) of the
-//      8 pixel rows into shared memory, at the rows' natural 16-byte phase (any width / base
-//      alignment);
+//   1. TMA into shared memory, mbarrier-completed: for 16-byte aligned inputs ONE tensor-map copy
+//      (cp.async.bulk.tensor.3d / UTMALDG) of the 8 x 768-byte tile, otherwise one bulk copy
+//      (cp.async.bulk / UBLKCP) per pixel row at the rows' natural 16-byte phase (any width / base
+//      alignment / pitch);
 //   2. cooperative luma pass: 4 pixels per lane-step (funnel-shift realign, PRMT, DP4A),
 //      bytes written to a 256 x 8 Y tile;
 //   3. the next strip's bulk copies are issued (the raw tile is free again) so their HBM
 //      latency overlaps the arithmetic below;
 //   4. one lane per 8x8 block, block entirely in registers: magic-number u8->f32,
-//      scaled even/odd butterfly DCT (rows then columns), quantization by one FFMA per
-//      bound (see below), zig-zag packing to int8 with PRMT, AC bit cost by table
-//      look-up, 4 x 128-bit stores of the 64 coefficients.
+//      scaled even/odd butterfly DCT (rows scalar, columns two at a time with packed fp32),
+//      quantization by one FFMA per bound (see below), zig-zag packing to int8 with PRMT, AC bit
+//      cost by table look-up in a loop over the bytes parked in shared memory (the hot loop has
+//      to fit the 32 KB instruction cache), 4 x 128-bit stores of the 64 coefficients.
 //
 // Bit-exactness.  The reference sums 64 products sequentially in fp32 with two unfused
 // multiplies per term; replaying that costs ~136 flop/pixel.  Instead the butterfly
