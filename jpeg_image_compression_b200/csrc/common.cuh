@@ -15,6 +15,9 @@ __constant__ float c_ref_scale[64];   // fl(fl(0.25f*C[u])*C[v])            (dct
 __constant__ float c_quant_f[64];     // (float)std_luminance_quant_tbl[i]   (quantization.c:35)
 // Fast path: q' = T[u][v] * c_rk[u*8+v], with T the scaled butterfly output.
 __constant__ float c_rk[64];
+// Tensor-core path: q' = t * c_rk_tc[k] with t the 2^21-scaled fixed-point sum of zig-zag position k
+// (two consecutive positions are read as one packed-fp32 operand)
+__constant__ float2 c_rk_tc[32];
 __constant__ uint8_t c_zigzag[64];    // raster index of zig-zag position k  (zigzag.c:7-15)
 __constant__ uint8_t c_dc_len[16];    // DC Huffman code length + size, per size class
 __constant__ uint32_t c_dc_code[16];  // (code << 8) | len, per size class
@@ -31,6 +34,31 @@ constexpr float kGammaA = 1.0431e-6f;     // 17.5 u
 constexpr float kGammaC = 6.1394e-6f;     // 103 u
 constexpr float kGamma0 = 2.9803e-5f;     // 500 u
 constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23: fmaf(x, r, kMagic) rounds x*r to nearest-even integer
+
+// Tensor-core transform (fused_block.cuh, TC = true): the 64-term sums are taken over the REFERENCE's own LUT
+// products, quantized to 22-bit fixed point (|W/2^21 - w| <= 2^-22 = 4u) and accumulated exactly, so the
+// "LUT vs ideal cosine" and "butterfly rounding" terms of the bound disappear:
+//   |s_ref - t/2^21|  <=  min( kTcGamma * A ,  kTcGammaA * A + kTcGammaC * Ac + kTcGamma0 )
+//   kTcGamma >= 76.2 u,  kTcGammaA >= 15.4 u,  kTcGammaC >= 74.2 u,  kTcGamma0 >= 430 u
+// The constants below are already multiplied by 2^21 (the kernel works in fixed-point units).
+constexpr float kTcScale = 2097152.0f;        // 2^21
+constexpr float kTcGamma = 4.5896e-6f * kTcScale;      // 77 u
+constexpr float kTcGammaA = 9.2387e-7f * kTcScale;     // 15.5 u
+constexpr float kTcGammaC = 4.4703e-6f * kTcScale;     // 75 u
+constexpr float kTcGamma0 = 2.6226e-5f * kTcScale;     // 440 u
+
+// one record per 32-block strip, written by K1
+struct __align__(8) StripRec {
+    uint32_t bits;      // bits of the strip's entropy-coded stream (an image's first strip: without its first DC symbol)
+    int16_t first_dc;   // quantized DC of the strip's first block
+    int16_t last_dc;    // quantized DC of the strip's last block
+};
+
+// device table block (one allocation per encoder)
+constexpr int TBL_SYM = 0;                       // uint32 [16][256] ready-made AC symbols (see build_tables)
+constexpr int TBL_DC_CODE = TBL_SYM + 16384;     // uint32 [16]   (code << 8) | len per DC size class
+constexpr int TBL_BMAT = TBL_DC_CODE + 128;      // fp16 [128 x 64] limb matrix of the tensor-core DCT, UMMA K-major layout
+constexpr int TBL_BYTES = TBL_BMAT + 16384;
 
 // error word bits (device -> host)
 enum : uint32_t {
@@ -123,6 +151,64 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+
+// ---- tcgen05 / tensor memory (5th-generation tensor cores) ---------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t columns)      // one whole warp
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)), "r"(columns) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t columns)           // the allocating warp
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(columns) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// shared-memory matrix descriptor, K-major, no swizzle: core matrices (8 rows x 16 bytes, contiguous) LBO bytes apart
+// along K and SBO bytes apart along M/N; descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, fp16 operands, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the mbarrier receives one arrival once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
+{
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+#define JB_TMEM_ST32(taddr, r)                                                                                         \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16," \
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),                   \
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),   \
+                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),       \
+                 "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),      \
+                 "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                   \
+                 : "memory")
+#define JB_TMEM_LD32(taddr, r)                                                                                         \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"       \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"                          \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),           \
+                   "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),         \
+                   "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),         \
+                   "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                              \
+                 : "r"(taddr)                                                                                          \
+                 : "memory")
 
 // decoupled look-back tile state: [63:42] epoch, [41:40] status, [39:0] value
 constexpr uint64_t LB_VALUE_MASK = (1ull << 40) - 1;

@@ -1,62 +1,86 @@
 // fused_block.cuh -- K1, the fused block kernel.
 //
-// One pass over the RGB payload: luma (converter.c:51) + edge replication
-// (converter.c:31,36) + level shift (converter.c:84-86) + 8x8 forward DCT (dct.c:63-96)
-// + quantization (quantization.c:34-36) + zig-zag (zigzag.c:51-60) + the AC part of the
-// block's Huffman bit cost (rle.c:83-123 with huffman.c code lengths).
+// One pass over the RGB payload: luma (converter.c:51) + edge replication (converter.c:31,36) + level shift
+// (converter.c:84-86) + 8x8 forward DCT (dct.c:63-96) + quantization (quantization.c:34-36) + zig-zag
+// (zigzag.c:51-60) + DC-difference / run-length symbols (rle.c:51-127) + Huffman codes and amplitude bits
+// (huffman.c:121-193) -- every coefficient is walked ONCE, here, and leaves the kernel as entropy-coded bits.
 //
-// Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels,
-// 6 KB of RGB).  One warp owns a strip:
+// Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels, 6 KB of RGB).  One warp owns
+// a strip, one lane a block:
 //   1. TMA into shared memory, mbarrier-completed: for 16-byte aligned inputs ONE tensor-map copy
-//      (cp.async.bulk.tensor.3d / UTMALDG) of the 8 x 768-byte tile, otherwise one bulk copy
-//      (cp.async.bulk / UBLKCP) per pixel row at the rows' natural 16-byte phase (any width / base
-//      alignment / pitch);
-//   2. cooperative luma pass: 4 pixels per lane-step (funnel-shift realign, PRMT, DP4A),
-//      bytes written to a 256 x 8 Y tile;
-//   3. the next strip's bulk copies are issued (the raw tile is free again) so their HBM
-//      latency overlaps the arithmetic below;
-//   4. one lane per 8x8 block, block entirely in registers: magic-number u8->f32,
-//      scaled even/odd butterfly DCT (rows scalar, columns two at a time with packed fp32),
-//      quantization by one FFMA per bound (see below), zig-zag packing to int8 with PRMT, AC bit
-//      cost by table look-up in a loop over the bytes parked in shared memory (the hot loop has
-//      to fit the 32 KB instruction cache), 4 x 128-bit stores of the 64 coefficients.
+//      (cp.async.bulk.tensor.3d / UTMALDG) of the 8 x 768-byte tile, otherwise one bulk copy (UBLKCP) per pixel row;
+//   2. cooperative luma pass: 4 pixels per lane-step (PRMT, DP4A), bytes written to a 256 x 8 Y tile; the next
+//      strip's copy is issued as soon as the raw tile has been read;
+//   3. transform + quantization, one of
+//      TC = true  (default): the 64-term sums of all 64 coefficients run on the tensor cores.  A tile of 128
+//                 blocks (4 strips = 4 warps) is one tcgen05.mma chain D[128 x 128] = A[128 x 64] * B^T: A = the
+//                 level-shifted luma values as fp16 integers, written by each lane for its block straight into
+//                 tensor memory (tcgen05.st); B = the reference's own LUT products cos[r][u]*cos[c][v] in 22-bit
+//                 fixed point, split into two 11-bit integer limbs held as fp16 (shared memory, UMMA K-major
+//                 layout).  Every product and partial sum is an integer below 2^24, so the fp32 accumulators in
+//                 TMEM hold the EXACT integer sums; tcgen05.ld hands each lane its block's 128 limb sums, 16
+//                 coefficients at a time, already in zig-zag order.  Everything after that is packed fp32
+//                 (FFMA2 / FADD2): limb combine, guard bracket, quantization.
+//      TC = false: scaled even/odd butterfly in registers (rows scalar, columns packed fp32), as in round 1.
+//      In both cases the value is bracketed (see below) and the few coefficients whose bracket straddles a rounding
+//      boundary are re-evaluated in the reference's exact operation order;
+//   4. entropy coding of the strip: non-zero map of the lane's block, bit cost by a walk over the non-zero
+//      coefficients only, warp scan -> bit offset of every block inside the strip, second walk emitting the Huffman
+//      code + amplitude bits of every symbol into the strip's bit window in shared memory (one table look-up per
+//      symbol), and the window goes to the strip's slot in global memory with 128-bit stores.  K2 only shifts the
+//      strips' streams to their global bit phase and stuffs.
 //
-// Bit-exactness.  The reference sums 64 products sequentially in fp32 with two unfused
-// multiplies per term; replaying that costs ~136 flop/pixel.  Instead the butterfly
-// value T (ideal cosines, FMA) is bracketed: the reference's sum s_ref satisfies
-// |s_ref - g*T| <= kGamma * A with A = sum|p| over the block (DESIGN.md section 3 derives the
-// bound: 65.1u*A for the reference's own roundings, 16u*A for the butterfly's, 15.7u*A
-// for the 6-decimal LUT vs ideal cosines, 6u*A for the scale/divide roundings, 102.8u*A in
-// total with u = 2^-24; the kernel takes the minimum with a mean-separated refinement,
-// u*(17.5*A + 103*Ac + 500), Ac = sum|p - mean|).  Quantization is monotone in s, so if
-// rounding (T-E)*rk and (T+E)*rk give the same integer that integer IS the reference's;
-// otherwise (about 2e-4 of the coefficients) the lane re-evaluates that one coefficient in
-// the reference's exact operation order (exact_quantized below).  The DC term is an exact integer sum in both
-// formulations and is quantized with the reference's own operation sequence.
+// Bit-exactness.  The reference sums 64 products sequentially in fp32 with two unfused multiplies per term;
+// replaying that costs ~136 flop/pixel.  Instead the fast value is bracketed: |s_ref - fast| <= gamma(A, Ac) with
+// A = sum|p| over the block and Ac = sum|p - mean| (DESIGN.md section 3 derives the constants for both transforms).
+// Quantization is monotone in s, so if rounding (t-E)*rk and (t+E)*rk gives the same integer that integer IS the
+// reference's; otherwise the lane re-evaluates that one coefficient in the reference's exact operation order
+// (exact_quantized).  The DC term is an exact integer sum in all formulations and is quantized with the reference's
+// own operation sequence.
 #pragma once
 
 #include <cuda.h>          // CUtensorMap (type only; the encoder function is looked up at run time)
 
 #include "common.cuh"
-#include "scan_pack.cuh"
 
 namespace jb {
 
-constexpr int K1_WARPS = 8;
-constexpr int K1_THREADS = K1_WARPS * 32;
-constexpr int K1_CTAS_PER_SM = 2;
 constexpr int RAW_PITCH = 784;                       // 768 payload + 16 bytes of alignment slack
 constexpr int RAW_BYTES = 8 * RAW_PITCH;             // 6272
 constexpr int Y_PITCH = 256;
 constexpr int Y_BYTES = 8 * Y_PITCH;                 // 2048
-constexpr int ZZ_PITCH = 17;                          // words per lane: 16 coefficient words + 1 (bank-conflict-free)
-constexpr int ZZ_BYTES = 32 * ZZ_PITCH * 4;          // 2176
 constexpr int HALO_BYTES = 256;                      // the raster-predecessor block's 8 x 24 RGB bytes (192), padded
-constexpr int K1_WARP_SMEM = RAW_BYTES + Y_BYTES + ZZ_BYTES + HALO_BYTES;    // 10752 = 84 x 128
-constexpr int ACLUT_BYTES = 16400;                   // 63 rows x 260 bytes + EOB length, then 16 DC lengths
-constexpr int K1_TABLE_BYTES = 16512;                // table area rounded up to 128 bytes: tensor-map copies need that alignment
-constexpr int K1_SMEM = K1_TABLE_BYTES + K1_WARPS * K1_WARP_SMEM;   // 102528: two CTAs per SM
 constexpr int TMAP_ROW_BYTES = 768;                  // a tensor-map box is dense: 8 rows x 768 bytes
+constexpr int K1_SYM_BYTES = 16384;                  // AC symbol table staged in shared memory
+constexpr int K1_BMAT_BYTES = 16384;                 // limb matrix of the tensor-core transform
+constexpr int STREAM_SMALL_BYTES = 1024;             // strip stream capacity of the default instantiation (32 B/block)
+constexpr int STREAM_BIG_BYTES = 5888;               // worst case: 32 blocks x 1463 bits = 5852 bytes
+
+// Launch shape and shared-memory carve-up of the four instantiations.
+//   TC:      one CTA per SM, warps in groups of four (a 128-block MMA tile); TMEM: 160 columns per group
+//   BIGWIN:  strip streams up to 184 bytes per block (any input); fewer warps fit
+template <bool TC, bool BIGWIN>
+struct K1Cfg {
+    static constexpr int WARPS = TC ? (BIGWIN ? 8 : 12) : 8;
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int CTAS_PER_SM = (TC || BIGWIN) ? 1 : 2;
+    static constexpr int GROUPS = WARPS / 4;
+    static constexpr int STREAM_BYTES = BIGWIN ? STREAM_BIG_BYTES : STREAM_SMALL_BYTES;
+    static constexpr int WIN_BYTES = STREAM_BYTES + 128;             // + slack: the bit writer may touch one word past the end
+    static constexpr int ZS_PITCH = (TC || BIGWIN) ? 20 : 17;        // words per lane of the coefficient staging area
+    static constexpr int ZS_BYTES = 32 * ZS_PITCH * 4;
+    static constexpr int WARP_SMEM = RAW_BYTES + Y_BYTES + ZS_BYTES + HALO_BYTES + WIN_BYTES;
+    static constexpr int TABLE_BYTES = K1_SYM_BYTES + (TC ? K1_BMAT_BYTES : 0);
+    static constexpr int SMEM = TABLE_BYTES + WARPS * WARP_SMEM;
+    static constexpr int TMEM_COLS = GROUPS == 3 ? 512 : 256;        // 160 per group, power of two
+    static_assert(WARP_SMEM % 128 == 0, "per-warp region must keep the tensor-map tiles 128-byte aligned");
+};
+constexpr int TC_GROUP_COLS = 160;                   // 128 accumulator columns (2 limbs x 64) + 32 columns of A
+constexpr uint32_t TC_IDESC = (1u << 4)              // D: fp32
+                              | (0u << 7) | (0u << 10)      // A, B: fp16
+                              | (0u << 15) | (0u << 16)     // both K-major
+                              | ((128u >> 3) << 17)         // N = 128
+                              | ((128u >> 4) << 24);        // M = 128
 
 // Everything a warp needs to know about one strip; computed once per strip (32-bit math).
 struct StripCtx {
@@ -74,7 +98,7 @@ struct StripCtx {
 };
 
 // position of a strip: image, block row, strip inside the block row.  Found by division once per warp and
-// then advanced incrementally (a warp's strips are `nwarps` apart).
+// then advanced incrementally (a warp's strips are a fixed distance apart).
 struct StripPos {
     uint32_t img, brow, sx;
 };
@@ -134,10 +158,10 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
     return c;
 }
 
-// stage the strip's 8 pixel rows: one TMA bulk copy per row (cp.async.bulk -> UBLKCP), lane r issuing
-// row r, all completed through the warp's mbarrier.  Each copy starts at the row's 16-byte-aligned
-// address and covers whole 16-byte chunks, so any width / base alignment works.  Also records the
-// rows' 16-byte phases in c.mispack.  Must be called by the whole warp.
+// stage the strip's 8 pixel rows: one tensor-map copy, or one TMA bulk copy per row (lane r issuing row r), completed
+// through the warp's mbarrier.  Each row copy starts at the row's 16-byte-aligned address and covers whole 16-byte
+// chunks, so any width / base alignment works.  Also records the rows' 16-byte phases in c.mispack.  Must be called
+// by the whole warp.
 __device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint8_t *hal, uint64_t *bar, int lane,
                                                   const CUtensorMap *tmap)
 {
@@ -233,11 +257,8 @@ __device__ __forceinline__ void dct8(float &x0, float &x1, float &x2, float &x3,
     x7 = fmaf(b3, -C1, fmaf(b2, C3, fmaf(b1, -C5, b0 * C7)));
 }
 
-// ---- the same butterfly on two columns at once (Blackwell packed fp32: FADD2 / FMUL2 / FFMA2) ----------
-// Element for element the operation sequence of dct8 (fma.rn.f32x2 etc. round each half like the scalar
-// instruction), so the guard-band analysis is unchanged; it halves the instruction count of the column
-// pass.  A pair lives in an aligned register pair, packing and unpacking are free.  The constants
-// come from constant memory (ptxas keeps them in uniform registers).
+// ---- Blackwell packed fp32 (FADD2 / FMUL2 / FFMA2): two fp32 lanes per instruction, each rounded like the scalar
+// instruction.  A pair lives in an aligned register pair, packing and unpacking are free. ------------------------
 typedef unsigned long long f32x2;
 __constant__ float2 c_dct2[9] = {
     {0.98078528040323044913f, 0.98078528040323044913f},   // 0: C1
@@ -255,7 +276,14 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi));
     return p;
 }
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi)
+{
+    f32x2 p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "r"(lo), "r"(hi));
+    return p;
+}
 __device__ __forceinline__ void unpack2(f32x2 p, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ void unpack2u(f32x2 p, uint32_t &lo, uint32_t &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p)); }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
 {
     f32x2 d;
@@ -304,143 +332,387 @@ __device__ __forceinline__ void dct8_2(f32x2 &x0, f32x2 &x1, f32x2 &x2, f32x2 &x
 // scale class of a frequency index: 0 -> g=1, 1 -> g=cos(pi/8), 2 -> g=cos(pi/4)
 __host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 : (k == 4 ? 2 : 0); }
 
-__global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
-k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ blkinfo,
-               StripRec *__restrict__ strips, uint32_t *__restrict__ strip_bits, const uint8_t *__restrict__ tables,
-               unsigned long long *__restrict__ flagged_counter, const int exact_mode,
-               uint64_t *__restrict__ lookback_state, const uint64_t lookback_words,
-               unsigned long long *__restrict__ trace, const __grid_constant__ CUtensorMap tmap_param)
+// ---- entropy coding helpers ------------------------------------------------------------------------------
+
+__device__ __forceinline__ int magnitude_class(int v)          // rle.c:9-22
 {
+    const int a = v < 0 ? -v : v;
+    return 32 - __clz(a);
+}
+
+// shared-memory accesses by 32-bit shared-space address: keeps the symbol loops free of the
+// generic-to-shared address arithmetic the compiler otherwise repeats at every access
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v, bool enable)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p red.shared.or.b32 [%0], %1;\n}"
+                 :: "r"(saddr), "r"(v), "r"((uint32_t)enable) : "memory");
+}
+
+// MSB-first bit appender with a 32-bit register accumulator, flushed word-wise into the zeroed
+// shared-memory window with OR-reductions (the first and last word of a block are shared with its
+// neighbours).  Branch-free: the flush is predicated.
+struct BitWriter {
+    uint32_t waddr;       // shared-space address of the window word being filled
+    uint32_t acc, fill;
+    __device__ __forceinline__ void start(uint32_t win_saddr, uint32_t relbit)
+    {
+        waddr = win_saddr + ((relbit >> 5) << 2);
+        fill = relbit & 31u;
+        acc = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t vl, uint32_t n)           // n in 1..27 bits, left-aligned in vl
+    {
+        acc |= vl >> fill;
+        fill += n;
+        const bool full = fill >= 32u;
+        red_or_shared(waddr, acc, full);
+        fill &= 31u;
+        waddr += full ? 4u : 0u;
+        acc = full ? vl << (n - fill) : acc;                               // the bits that did not fit (none if fill == 0)
+    }
+    __device__ __forceinline__ void finish() { red_or_shared(waddr, acc, fill != 0u); }
+};
+
+// 4-bit mask of the non-zero bytes of a word (bit j <-> byte j)
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
+{
+    const uint32_t t = (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;   // 0x80 per non-zero byte
+    return (t * 0x00204081u) >> 28;                                             // gather bits 7,15,23,31
+}
+
+// Bit cost of a block's AC symbols (rle.c:83-123 with the code lengths of huffman.c:89-104): the lane visits only
+// the non-zero coefficients (map mlo/mhi, bit k <-> zig-zag position k); each visit is one look-up in the symbol
+// table sym[run & 15][value & 255], whose low 5 bits are the symbol's length (code + amplitude bits).
+// zs: shared-space address of the block's 64 coefficient bytes.  Returns the bits; `last` = position of the last non-zero.
+__device__ __forceinline__ uint32_t ac_cost(uint32_t zs, uint32_t mlo, uint32_t mhi, uint32_t sym, uint32_t zrl_len,
+                                            uint32_t eob_len, int &last)
+{
+    uint32_t bits = 0;
+    int prev = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? mhi : mlo;
+#pragma unroll 1
+        while (m) {
+            const int k = 32 * half + __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint32_t byte = lds_u8(zs + (uint32_t)k);
+            const uint32_t run = (uint32_t)(k - prev - 1);
+            prev = k;
+            bits += (run >> 4) * zrl_len + (lds_u32(sym + 4u * (((run & 15u) << 8) | byte)) & 31u);   // ZRLs: rle.c:99-103
+        }
+    }
+    last = prev;
+    if (prev < 63) bits += eob_len;                                                   // EOB, rle.c:121-123
+    return bits;
+}
+
+// Emit one block's symbols (rle.c:59-124 -> huffman.c:145-173) through the bit writer.  sym[run][value] holds
+// (Huffman code << size | amplitude bits) left-aligned with the total length in the low 5 bits, i.e. huffman.c:164-173
+// applied to the symbol rle.c:106-113 would have produced; slot [0][0] carries EOB and [0][0x80] ZRL.
+__device__ __forceinline__ void emit_block(BitWriter &bw, uint32_t zs, bool with_dc, int diff, uint32_t dc_entry, uint32_t mlo,
+                                           uint32_t mhi, uint32_t sym)
+{
+    if (with_dc) {                                                                    // rle.c:68-76
+        const int sz = magnitude_class(diff);
+        const uint32_t amp = (uint32_t)(diff > 0 ? diff : diff - 1) & ((1u << sz) - 1u);   // rle.c:24-35, huffman.c:39
+        const uint32_t n = (dc_entry & 0xFFu) + (uint32_t)sz;
+        bw.put((((dc_entry >> 8) << sz) | amp) << (32u - n), n);
+    }
+    int prev = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? mhi : mlo;
+#pragma unroll 1
+        while (m) {
+            const int k = 32 * half + __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint32_t byte = lds_u8(zs + (uint32_t)k);
+            int run = k - prev - 1;
+            prev = k;
+            if (run >= 16) {                                                           // ZRL, rle.c:99-103
+                const uint32_t z = lds_u32(sym + 4u * 0x80u);
+                do {
+                    bw.put(z & ~31u, z & 31u);
+                    run -= 16;
+                } while (run >= 16);
+            }
+            const uint32_t e = lds_u32(sym + 4u * (((uint32_t)run << 8) | byte));
+            bw.put(e & ~31u, e & 31u);
+        }
+    }
+    if (prev < 63) {                                                                   // EOB, rle.c:121-123
+        const uint32_t e = lds_u32(sym);
+        bw.put(e & ~31u, e & 31u);
+    }
+    bw.finish();
+}
+
+// what K1 leaves behind
+struct K1Out {
+    StripRec *strips;              // [total_strips]
+    uint32_t *strip_bits;          // [total_strips] compact copy of StripRec.bits
+    uint8_t *streams;              // [total_strips][slot_bytes]: the strip's bits, MSB first in 32-bit words
+    uint32_t slot_bytes;           // multiple of 16, <= the instantiation's STREAM_BYTES
+    int8_t *dbg_coef;              // optional stage tap: [blocks][64] zig-zag int8
+    uint32_t *dbg_blkinfo;         // optional stage tap: bit offset inside the strip | last non-zero << 16
+    unsigned long long *flagged;   // coefficients re-evaluated in reference order (statistics)
+    uint32_t *err;
+};
+
+template <bool TC, bool BIGWIN>
+__global__ void __launch_bounds__(K1Cfg<TC, BIGWIN>::THREADS, K1Cfg<TC, BIGWIN>::CTAS_PER_SM)
+k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, const int exact_mode,
+               uint64_t *__restrict__ lookback_state, const uint64_t lookback_words, unsigned long long *__restrict__ trace,
+               const __grid_constant__ CUtensorMap tmap_param)
+{
+    using Cfg = K1Cfg<TC, BIGWIN>;
+    constexpr int WARPS = Cfg::WARPS;
 #ifdef JPEGB200_TRACE   // tracing build only (make trace -> libjpegb200_trace.so)
-#define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * K1_WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
+#define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
 #else
 #define K1_TRACE(slot) do { } while (0)
 #endif
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *aclut = smem;
-    const uint8_t *s_dclen = smem + TBL_DC_LEN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *raw = smem + K1_TABLE_BYTES + warp * K1_WARP_SMEM;
+    uint8_t *raw = smem + Cfg::TABLE_BYTES + warp * Cfg::WARP_SMEM;
     const CUtensorMap *tmap = g.use_tmap ? &tmap_param : nullptr;
     const uint32_t raw_pitch = g.use_tmap ? TMAP_ROW_BYTES : RAW_PITCH;
     uint8_t *ybuf = raw + RAW_BYTES;
-    uint32_t *zs = reinterpret_cast<uint32_t *>(ybuf + Y_BYTES) + lane * ZZ_PITCH;   // this lane's 64 coefficient bytes
-    uint8_t *hal = ybuf + Y_BYTES + ZZ_BYTES;                    // predecessor block, tensor-map path only
+    uint32_t *zs = reinterpret_cast<uint32_t *>(ybuf + Y_BYTES) + lane * Cfg::ZS_PITCH;   // this lane's 64 coefficient bytes
+    uint8_t *hal = ybuf + Y_BYTES + Cfg::ZS_BYTES;               // predecessor block, tensor-map path only
+    uint32_t *win = reinterpret_cast<uint32_t *>(hal + HALO_BYTES);   // the strip's bit window
+    uint32_t smem_sa = smem_u32(smem);
+    asm volatile("mov.b32 %0, %0;" : "+r"(smem_sa));             // opaque: computed once, not rematerialised at every use
+    const uint32_t sym_sa = smem_sa;                             // symbol table at offset 0
+    const uint32_t zs_sa = smem_sa + (uint32_t)(reinterpret_cast<uint8_t *>(zs) - smem);
+    const uint32_t win_sa = smem_sa + (uint32_t)(reinterpret_cast<uint8_t *>(win) - smem);
+    __shared__ uint32_t s_dc[16];                                // DC codes: (code << 8) | len per size class
+    __shared__ __align__(8) uint64_t s_bar[WARPS + 1 + 3];       // per-warp tile barriers, the table barrier, per-group MMA barriers
+    __shared__ uint32_t s_tmem;
 
     K1_TRACE(0);
-    // Static schedule: persistent warp i takes strips i, i + nwarps, ...; the 8 warps of a CTA work on 8
-    // consecutive strips (contiguous 6 KB runs of the same pixel rows).  Measured alternatives: interleaving
-    // warp indices across CTAs balances a partial last round over the SMs but loses that locality (+4 %
-    // time); handing strips out by ticket cannot balance a ~2-round image either, because the next strip
-    // must be known a whole strip ahead for the prefetch.
-    const uint32_t nwarps = gridDim.x * K1_WARPS;
+    // Static schedule.  TC: a group of four warps takes tiles of four consecutive strips, tile = group index, + number of
+    // groups, ...; otherwise persistent warp i takes strips i, i + nwarps, ....  Either way the warps of a CTA work on
+    // consecutive strips (contiguous 6 KB runs of the same pixel rows).
     const uint32_t total = (uint32_t)g.total_strips;
-    uint32_t s = blockIdx.x * K1_WARPS + warp;
-    __shared__ __align__(8) uint64_t s_bar[K1_WARPS + 1];      // one mbarrier per warp (pixel tiles) + one for the table
+    const uint32_t stride = gridDim.x * WARPS;                   // distance between a warp's strips
+    uint32_t s = blockIdx.x * WARPS + warp;
+    uint32_t tile_s0 = TC ? (s & ~3u) : s;                       // group-uniform loop variable
     uint64_t *bar = &s_bar[warp];
+    uint64_t *table_bar = &s_bar[WARPS];
     if (lane == 0) mbar_init(bar, g.use_tmap ? 33 : 1);          // tensor-map path: + one asynchronous arrival per lane
-    if (threadIdx.x == 0) mbar_init(&s_bar[K1_WARPS], 1);
+    if (threadIdx.x == 0) {
+        mbar_init(table_bar, 1);
+        if (TC)
+            for (int i = 0; i < Cfg::GROUPS; ++i) mbar_init(&s_bar[WARPS + 1 + i], 1);
+    }
+    if (threadIdx.x < 16) s_dc[threadIdx.x] = reinterpret_cast<const uint32_t *>(tables + TBL_DC_CODE)[threadIdx.x];
     mbar_fence_init();
+    if (TC && warp == 0) tmem_alloc(&s_tmem, Cfg::TMEM_COLS);
+    if (TC) tc_fence_before_sync();
     __syncthreads();
+    if (TC) tc_fence_after_sync();
     uint32_t phase = 0;
     StripCtx cur;
     StripPos pos;
-    const uint32_t dq = nwarps / (uint32_t)g.spr, dr = nwarps - dq * (uint32_t)g.spr;
+    const uint32_t dq = stride / (uint32_t)g.spr, dr = stride - dq * (uint32_t)g.spr;
     if (s < total) {
         pos = strip_pos(g, s);
         cur = strip_ctx(g, pos);
         strip_issue_loads(cur, raw, hal, bar, lane, tmap);                  // first strip's pixels are in flight ...
     }
-    if (threadIdx.x == 0) {                                      // ... while the bit-cost table is staged (one 16 KB bulk copy)
-        mbar_expect_tx(&s_bar[K1_WARPS], ACLUT_BYTES);
-        bulk_g2s(aclut, tables + TBL_ACLUT, ACLUT_BYTES, &s_bar[K1_WARPS]);
+    if (threadIdx.x == 0) {                                      // ... while the tables are staged (TMA bulk copies)
+        mbar_expect_tx(table_bar, Cfg::TABLE_BYTES);
+        bulk_g2s(smem, tables + TBL_SYM, K1_SYM_BYTES, table_bar);
+        if (TC) bulk_g2s(smem + K1_SYM_BYTES, tables + TBL_BMAT, K1_BMAT_BYTES, table_bar);
     }
     // reset the look-back state of the entropy kernel (K2) that follows in the stream: keeps a
     // whole encode at two launches and CUDA-graph replayable
-    for (uint64_t i = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x; i < lookback_words;
-         i += (uint64_t)gridDim.x * K1_THREADS)
+    for (uint64_t i = (uint64_t)blockIdx.x * Cfg::THREADS + threadIdx.x; i < lookback_words;
+         i += (uint64_t)gridDim.x * Cfg::THREADS)
         lookback_state[i] = 0;
     bool table_ready = false;                                    // waited for at its first use
     K1_TRACE(1);
 
+    // tensor memory of this warp's group: accumulators at column 160 * group, A at + 128; the warp owns lanes 32 * (warp % 4)
+    const int group = warp >> 2, quad = warp & 3;
+    const uint32_t tmem_d = TC ? s_tmem + (uint32_t)(group * TC_GROUP_COLS) : 0u;
+    const uint32_t tmem_a = tmem_d + 128u;
+    const uint32_t tmem_lane = (uint32_t)(quad * 32) << 16;
+    uint64_t *mma_bar = &s_bar[WARPS + 1 + group];
+    uint32_t mma_phase = 0;
+
     uint32_t nflag = 0;
     const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
+    const uint32_t cap_bits = o.slot_bytes * 8u;
     float magic;                                     // 1.5 * 2^23 held in a register: leaves the FFMA's
-    asm("mov.f32 %0, 0f4B400000;" : "=f"(magic));     // constant-bank slot to the quantizer constant c_rk
+    asm("mov.f32 %0, 0f4B400000;" : "=f"(magic));     // constant-bank slot to the quantizer constant
 
-    for (; s < total; s += nwarps) {
-        // luma sum of the raster-predecessor block: lane l covers row l/4, columns 2*(l%4) and +1;
-        // the loads are issued now and consumed after the transform
+    for (; tile_s0 < total; tile_s0 += stride, s += stride) {
+        const bool valid = s < total;                            // TC: the last tile may have idle warps
         uint32_t halo_y = 0;
-        if (cur.halo && !tmap) {
-            const uint8_t *hp = cur.halo + (int64_t)min(lane >> 2, cur.halo_rmax) * cur.pitch;
-            const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
-            const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
-            halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        if (cur.halo && tmap) {                          // same sum from the block staged in shared memory
-            const uint8_t *hp = hal + 24 * (lane >> 2);
-            const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
-            const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
-            halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
-        }
-        if (!table_ready) K1_TRACE(2);
-
-        // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
-        if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
-            // full strip, word-aligned rows: 3 LDS + DP4A/PRMT per 4 pixels.  Two rows per trip, not fully
-            // unrolled: the kernel's hot loop has to stay inside the 32 KB instruction cache (L1.5)
-#pragma unroll 2
-            for (int r = 0; r < 8; ++r) {
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
-                uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
-                yo[lane] = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi);
-                yo[lane + 32] = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
+        StripCtx me = cur;
+        uint32_t yw[16];                                         // the lane's 64 luma bytes (TC)
+        uint32_t absdev = 0, absmean = 0;                        // A = sum |Y - 128|, Ac = sum |Y - mean|
+        float x00 = 0.0f;                                        // sum (Y - 128), exact
+        if (valid) {
+            // luma sum of the raster-predecessor block: lane l covers row l/4, columns 2*(l%4) and +1;
+            // the loads are issued now and consumed after the transform
+            if (cur.halo && !tmap) {
+                const uint8_t *hp = cur.halo + (int64_t)min(lane >> 2, cur.halo_rmax) * cur.pitch;
+                const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
+                const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
+                halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
             }
-        } else {
-            // any width / any base alignment: funnel-shift the row to word alignment
-            const int ngroups = (cur.npx + 3) >> 2;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            if (cur.halo && tmap) {                          // same sum from the block staged in shared memory
+                const uint8_t *hp = hal + 24 * (lane >> 2);
+                const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
+                const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
+                halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
+            }
+            if (!table_ready) K1_TRACE(2);
+
+            // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
+            if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
+                // full strip, word-aligned rows: 3 LDS + DP4A/PRMT per 4 pixels.  Two rows per trip, not fully
+                // unrolled: the kernel's hot loop has to stay inside the 32 KB instruction cache (L1.5)
+#pragma unroll 2
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
+                    uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
+                    yo[lane] = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi);
+                    yo[lane + 32] = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
+                }
+            } else {
+                // any width / any base alignment: funnel-shift the row to word alignment
+                const int ngroups = (cur.npx + 3) >> 2;
 #pragma unroll 1
-            for (int item = lane; item < 512; item += 32) {
-                const int r = item >> 6, gc = item & 63;
-                if (gc < ngroups) {
-                    const uint32_t mis = (cur.mispack >> (4 * r)) & 15u;
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch) + (mis >> 2) + 3 * gc;
-                    const uint32_t sh = (mis & 3u) * 8u;
-                    const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
-                    reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] =
-                        luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh), g.wt_lo, g.wt_hi);
+                for (int item = lane; item < 512; item += 32) {
+                    const int r = item >> 6, gc = item & 63;
+                    if (gc < ngroups) {
+                        const uint32_t mis = (cur.mispack >> (4 * r)) & 15u;
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch) + (mis >> 2) + 3 * gc;
+                        const uint32_t sh = (mis & 3u) * 8u;
+                        const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
+                        reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] =
+                            luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh), g.wt_lo, g.wt_hi);
+                    }
                 }
             }
-        }
-        __syncwarp();
-
-        // raw tile is free: prefetch the next strip while this one is transformed
-        const StripCtx me = cur;
-        if (s + nwarps < total) {
-            strip_advance(g, pos, dq, dr);
-            cur = strip_ctx(g, pos);
-            strip_issue_loads(cur, raw, hal, bar, lane, tmap);
-        }
-
-        // right-edge replication inside the last real block (converter.c:36)
-        const int padpx = me.vb * 8 - me.npx;
-        if (padpx > 0) {
-            if (lane < padpx) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) ybuf[r * Y_PITCH + me.npx + lane] = ybuf[r * Y_PITCH + me.npx - 1];
-            }
             __syncwarp();
-        }
 
-        uint32_t my_bits = 0, my_last = 0;                     // this lane's block: bit cost, last non-zero AC index
-        int my_dc = 0;
-        if (lane < me.vb) {
-            const uint8_t *yblk = ybuf + lane * 8;
+            // raw tile is free: prefetch the next strip while this one is transformed
+            if (s + stride < total) {
+                strip_advance(g, pos, dq, dr);
+                cur = strip_ctx(g, pos);
+                strip_issue_loads(cur, raw, hal, bar, lane, tmap);
+            }
+
+            // right-edge replication inside the last real block (converter.c:36)
+            const int padpx = me.vb * 8 - me.npx;
+            if (padpx > 0) {
+                if (lane < padpx) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) ybuf[r * Y_PITCH + me.npx + lane] = ybuf[r * Y_PITCH + me.npx - 1];
+                }
+                __syncwarp();
+            }
+        }
+        const uint8_t *yblk = ybuf + lane * 8;
+
+        uint32_t zw[16], xw[16];                                 // quantized coefficients (zig-zag, int8) / bracket disagreement
+        if (TC) {
+            // ---- A operand: the block's 64 level-shifted luma values as fp16, K order = raster, into tensor memory --
+            if (valid) {
+                uint32_t sumy = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
+                    yw[2 * r] = v.x;
+                    yw[2 * r + 1] = v.y;
+                    absdev = __vsadu4(v.x, 0x80808080u) + absdev;
+                    absdev = __vsadu4(v.y, 0x80808080u) + absdev;
+                    sumy = __vsadu4(v.x, 0u) + sumy;
+                    sumy = __vsadu4(v.y, 0u) + sumy;
+                }
+                uint32_t ar[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    // 0x64yy is the fp16 1024 + yy; subtracting 1152 is exact: yy - 128 (converter.c:84)
+                    const uint32_t lo = __byte_perm(yw[j], 0x64646464u, 0x4140u), hi = __byte_perm(yw[j], 0x64646464u, 0x4342u);
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(ar[2 * j]) : "r"(lo), "r"(0xE480E480u));
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(ar[2 * j + 1]) : "r"(hi), "r"(0xE480E480u));
+                }
+                JB_TMEM_ST32(tmem_a + tmem_lane, ar);
+                tmem_wait_st();
+                x00 = (float)((int)sumy - 8192);
+                // Ac = sum |Y - m|, m = the block's rounded mean luma
+                const int mean = (int)rintf(x00 * 0.015625f) + 128;
+                const uint32_t m4 = (uint32_t)mean * 0x01010101u;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) absmean = __vsadu4(yw[j], m4) + absmean;
+            }
+            tc_fence_before_sync();
+            named_bar_sync(1 + group, 128);                      // the tile's four A quarters are in tensor memory
+            if (quad == 0 && lane == 0) {
+                if (!table_ready) mbar_wait(table_bar, 0);
+                tc_fence_after_sync();
+                const uint32_t b_sa = smem_sa + K1_SYM_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)                   // K = 64 in four steps of 16; B: 4 KB per step, LBO 128, SBO 256
+                    umma_f16_ts(tmem_d, tmem_a + 8u * ks, umma_desc(b_sa + 4096u * ks, 128u, 256u), TC_IDESC, ks > 0 ? 1u : 0u);
+                umma_commit(mma_bar);
+            }
+            if (valid) {
+                mbar_wait(mma_bar, mma_phase);
+                tc_fence_after_sync();
+                // guard half-width in fixed-point units
+                const float eb = fminf((float)absdev * kTcGamma, fmaf((float)absdev, kTcGammaA, fmaf((float)absmean, kTcGammaC, kTcGamma0)));
+                const f32x2 e2 = pack2(eb, eb), k2048 = pack2(2048.0f, 2048.0f), m2 = pack2(magic, magic);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                    // 16 coefficients = 4 zig-zag words per TMEM load
+                    uint32_t r[32];
+                    JB_TMEM_LD32(tmem_d + tmem_lane + 32u * c, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int wi = 0; wi < 4; ++wi) {
+                        // columns 8wi..: S0(a) S0(b) S1(a) S1(b) S0(c) S0(d) S1(c) S1(d), (a..d) = zig-zag positions 4w..4w+3
+                        uint32_t hb[4], lb[4];
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            const f32x2 s0 = pack2u(r[8 * wi + 4 * p], r[8 * wi + 4 * p + 1]);
+                            const f32x2 s1 = pack2u(r[8 * wi + 4 * p + 2], r[8 * wi + 4 * p + 3]);
+                            const f32x2 t = fma2(s0, k2048, s1);                       // the 2^21-scaled sum of products
+                            const f32x2 rk = *reinterpret_cast<const f32x2 *>(&c_rk_tc[8 * c + 2 * wi + p]);
+                            unpack2u(fma2(add2(t, e2), rk, m2), hb[2 * p], hb[2 * p + 1]);
+                            unpack2u(fma2(sub2(t, e2), rk, m2), lb[2 * p], lb[2 * p + 1]);
+                        }
+                        const uint32_t h = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040u), __byte_perm(hb[2], hb[3], 0x0040u), 0x5410u);
+                        const uint32_t l = __byte_perm(__byte_perm(lb[0], lb[1], 0x0040u), __byte_perm(lb[2], lb[3], 0x0040u), 0x5410u);
+                        zw[4 * c + wi] = h;
+                        xw[4 * c + wi] = (h ^ l) | xforce;
+                    }
+                }
+                tc_fence_before_sync();                          // orders these loads before the next tile's MMA (through the group barrier)
+            }
+            mma_phase ^= 1u;
+        } else if (valid) {
             float x[8][8];
-            uint32_t absdev = 0;                                   // A = sum |Y - 128|
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const uint2 v = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
@@ -469,11 +741,9 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
 #pragma unroll
                 for (int r = 0; r < 8; ++r) unpack2(p[r], x[r][c], x[r][c + 1]);
             }
-
-            // Ac = sum |Y - m|, m = the block's rounded mean luma (from the exact DC sum)
-            uint32_t absmean = 0;
+            x00 = x[0][0];
             {
-                const int mean = (int)rintf(x[0][0] * 0.015625f) + 128;
+                const int mean = (int)rintf(x00 * 0.015625f) + 128;
                 const uint32_t m4 = (uint32_t)mean * 0x01010101u;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -492,9 +762,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
 #pragma unroll
                     for (int b = 0; b < 3; ++b) ecls[a][b] = eb * (IG[a] * IG[b] * 1.000001f);
             }
-
             // quantize in zig-zag order, pack to int8 (low byte of the magic-biased float)
-            uint32_t zw[16], xw[16];
 #pragma unroll
             for (int w = 0; w < 16; ++w) {
                 uint32_t hb[4], lb[4];
@@ -504,10 +772,10 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                                                 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
                                                 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
                                                 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-                    const int pos = ZZ[4 * w + j], u = pos >> 3, v = pos & 7;
+                    const int zpos = ZZ[4 * w + j], u = zpos >> 3, v = zpos & 7;
                     const float t = x[u][v];
                     const float e = ecls[gclass(u)][gclass(v)];
-                    const float rk = c_rk[pos];
+                    const float rk = c_rk[zpos];
                     hb[j] = __float_as_uint(fmaf(__fadd_rn(t, e), rk, magic));
                     lb[j] = __float_as_uint(fmaf(__fadd_rn(t, -e), rk, magic));
                 }
@@ -516,16 +784,21 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 zw[w] = h;
                 xw[w] = (h ^ l) | xforce;
             }
+        }
+        if (!valid) continue;                                    // (TC only) idle warp of the last tile: barriers done
 
-            // DC: exact integer sum in both formulations; reference operation sequence
+        uint32_t my_bits = 0, mlo = 0, mhi = 0;                  // this lane's block: bit cost, non-zero map of its AC coefficients
+        int my_last = 0, my_dc = 0;
+        if (lane < me.vb) {
+            // DC: exact integer sum in all formulations; reference operation sequence
             // fl(k00 * S) / 16 then roundf (dct.c:93, quantization.c:36)
             {
-                const float f = __fmul_rn(c_ref_scale[0], x[0][0]);
+                const float f = __fmul_rn(c_ref_scale[0], x00);
                 const int dcq = (int)roundf(f * 0.0625f);
                 zw[0] = (zw[0] & 0xFFFFFF00u) | ((uint32_t)dcq & 0xFFu);
                 xw[0] &= 0xFFFFFF00u;
+                my_dc = dcq;
             }
-
             uint32_t anyx = 0;
 #pragma unroll
             for (int w = 0; w < 16; ++w) anyx |= xw[w];
@@ -541,8 +814,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                 while (fm) {
                     const int k = __ffsll((long long)fm) - 1;
                     fm &= fm - 1;
-                    const int pos = c_zigzag[k];
-                    const uint32_t q = (uint32_t)exact_quantized(yblk, pos >> 3, pos & 7) & 0xFFu;
+                    const int zpos = c_zigzag[k];
+                    const uint32_t q = (uint32_t)exact_quantized(yblk, zpos >> 3, zpos & 7) & 0xFFu;
                     const uint32_t sh = 8u * (uint32_t)(k & 3), keep = ~(0xFFu << sh), ins = q << sh;
                     const int kw = k >> 2;
 #pragma unroll
@@ -551,97 +824,124 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ b
                     ++nflag;
                 }
             }
-
-            if (!table_ready) {
-                K1_TRACE(3);
-                mbar_wait(&s_bar[K1_WARPS], 0);                    // the bit-cost table, staged during the first transform
-                K1_TRACE(4);
-            }
-            // AC bit cost: code length + amplitude bits per non-zero coefficient, ZRLs, EOB
-            // The walk is a real loop over bytes parked in shared memory, not 63 unrolled copies reading
-            // registers: the kernel's hot loop has to fit the SM's 32 KB instruction cache, otherwise the 16
-            // warps (each at its own place in the code) saturate the GPC-level instruction cache.
+            // park the coefficient bytes in shared memory (the symbol walks index them by position) and build the
+            // 63-bit map of the non-zero AC coefficients
+            if (Cfg::ZS_PITCH % 4 == 0) {
 #pragma unroll
-            for (int w = 0; w < 16; ++w) zs[w] = zw[w];
-            const uint8_t *zb = reinterpret_cast<const uint8_t *>(zs);
-            uint32_t bits = 0, lastk = 0;                          // lastk = ACLUT_STRIDE * (index of the last non-zero)
-            const uint8_t *lut = aclut;                            // row of zero run 0 for position k
-#pragma unroll 21                     // 3 trips: measured best between code size (instruction cache) and loop overhead
-            for (int k = 1; k < 64; ++k) {
-                const uint32_t byte = zb[k];
-                bits += lut[byte - lastk];
-                lut += ACLUT_STRIDE;
-                if (byte != 0) lastk = (uint32_t)(lut - aclut);   // = k * ACLUT_STRIDE
+                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4 *>(zs)[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; ++w) zs[w] = zw[w];
             }
-            my_last = (lastk * 253u) >> 16;                        // lastk / 260 for lastk <= 63*260
-            if (my_last != 63u) bits += aclut[ACLUT_ROWS * ACLUT_STRIDE];   // EOB code length (rle.c:121-123)
-            my_bits = bits;
-            my_dc = (int)(int8_t)(zw[0] & 0xFFu);
-
-            uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 64);
-            dst[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
-            dst[1] = make_uint4(zw[4], zw[5], zw[6], zw[7]);
-            dst[2] = make_uint4(zw[8], zw[9], zw[10], zw[11]);
-            dst[3] = make_uint4(zw[12], zw[13], zw[14], zw[15]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t m16 = nonzero_nibble(zw[4 * i]) | (nonzero_nibble(zw[4 * i + 1]) << 4) | (nonzero_nibble(zw[4 * i + 2]) << 8) |
+                                     (nonzero_nibble(zw[4 * i + 3]) << 12);
+                if (i < 2) mlo |= m16 << (16 * i);
+                else mhi |= m16 << (16 * (i - 2));
+            }
+            mlo &= ~1u;                                          // position 0 is the DC
         }
         if (!table_ready) {
-            mbar_wait(&s_bar[K1_WARPS], 0);                        // lanes without a block; immediate for the others
+            K1_TRACE(3);
+            mbar_wait(table_bar, 0);                             // the symbol table, staged during the first transform
             table_ready = true;
-            K1_TRACE(5);
+            K1_TRACE(4);
         }
-        // DC-difference costs (rle.c:68-76).  The strip's first block is predicted from the block
-        // before the strip, whose quantized DC follows from its 64 luma values alone (an exact integer
-        // sum, same closed form as above).  The very first strip of an image is charged by K2 (its
-        // predictor is 0, or the previous stripe's last DC in multi-GPU runs).
+        __syncwarp();
+        if (lane < me.vb) {
+            const uint32_t zrl = lds_u32(sym_sa + 4u * 0x80u) & 31u, eob = lds_u32(sym_sa) & 31u;
+            my_bits = ac_cost(zs_sa, mlo, mhi, sym_sa, zrl, eob, my_last);
+        }
+        // DC differences (rle.c:68-76).  The strip's first block is predicted from the block before the strip, whose
+        // quantized DC follows from its 64 luma values alone (an exact integer sum, same closed form as above).  The
+        // very first block of an image is coded by K2 (its predictor is 0, or the previous stripe's last DC in
+        // multi-GPU runs).
+        int diff;
+        bool with_dc;
+        uint32_t dc_entry = 0;
         {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) halo_y += __shfl_xor_sync(0xffffffffu, halo_y, o);
+            for (int ofs = 16; ofs > 0; ofs >>= 1) halo_y += __shfl_xor_sync(0xffffffffu, halo_y, ofs);
             int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
             if (lane == 0) {
                 const float f = __fmul_rn(c_ref_scale[0], (float)((int)halo_y - 8192));
                 prev_dc = (int)roundf(f * 0.0625f);
             }
-            if (lane < me.vb && (lane > 0 || me.halo)) my_bits += s_dclen[magnitude_class(my_dc - prev_dc)];
-            uint32_t incl = my_bits;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
+            diff = my_dc - prev_dc;
+            with_dc = lane < me.vb && (lane > 0 || me.halo);
+            if (with_dc) {
+                const int sz = magnitude_class(diff);
+                dc_entry = s_dc[sz];
+                my_bits += (dc_entry & 0xFFu) + (uint32_t)sz;
             }
+        }
+        uint32_t incl = my_bits;
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, ofs);
+            if (lane >= ofs) incl += n;
+        }
+        const uint32_t strip_total = __shfl_sync(0xffffffffu, incl, 31);
+        const bool fits = strip_total <= cap_bits;
+        const uint32_t nquads = fits ? (strip_total + 127u) >> 7 : 0u;               // 16-byte units written to the slot
+        // ---- emit the strip's bits into the zeroed window, then window -> the strip's slot ------------------------
+        for (uint32_t i = lane; i < nquads + 1; i += 32) reinterpret_cast<uint4 *>(win)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        if (fits && lane < me.vb) {
+            BitWriter bw;
+            bw.start(win_sa, incl - my_bits);
+            emit_block(bw, zs_sa, with_dc, diff, dc_entry, mlo, mhi, sym_sa);
+        }
+        __syncwarp();
+        {
+            uint4 *dst = reinterpret_cast<uint4 *>(o.streams + (uint64_t)s * o.slot_bytes);
+            for (uint32_t i = lane; i < nquads; i += 32) dst[i] = reinterpret_cast<const uint4 *>(win)[i];
             const int first_dc = __shfl_sync(0xffffffffu, my_dc, 0);
-            if (lane < me.vb) blkinfo[me.block0 + (uint32_t)lane] = blk_pack(incl - my_bits, my_last);
             if (lane == me.vb - 1) {
-                strips[s] = StripRec{incl, (int16_t)first_dc, (int16_t)my_dc};
-                strip_bits[s] = incl;
+                o.strips[s] = StripRec{strip_total, (int16_t)first_dc, (int16_t)my_dc};
+                o.strip_bits[s] = strip_total;
+                if (!fits) atomicOr(o.err, ERRBIT_WORKSPACE);
+            }
+            if (o.dbg_coef && lane < me.vb) {                    // stage taps for the parity tests
+                uint4 *cd = reinterpret_cast<uint4 *>(o.dbg_coef + (me.block0 + (uint32_t)lane) * 64);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cd[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
+                o.dbg_blkinfo[me.block0 + (uint32_t)lane] = (incl - my_bits) | ((uint32_t)my_last << 16);
             }
         }
         __syncwarp();
 #ifdef JPEGB200_TRACE
         // second half of the trace buffer: completion times of this warp's first 8 strips
         if (trace && lane == 0) {
-            const uint32_t it = (s - (blockIdx.x * K1_WARPS + warp)) / nwarps;
-            if (it < 8) trace[(uint64_t)(nwarps + blockIdx.x * K1_WARPS + warp) * 8 + it] = globaltimer_ns();
+            const uint32_t it = (s - (blockIdx.x * WARPS + warp)) / stride;
+            if (it < 8) trace[(uint64_t)(stride + blockIdx.x * WARPS + warp) * 8 + it] = globaltimer_ns();
         }
 #endif
     }
 
     K1_TRACE(6);
 #ifdef JPEGB200_TRACE
-    {   // slot 7: strips done * 1000 + coefficients this warp re-evaluated on the exact path
+    {   // slot 7: coefficients this warp re-evaluated on the exact path
         uint32_t nf = nflag;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
-        if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * K1_WARPS + warp) * 8 + 7] = nf;
+        for (int ofs = 16; ofs > 0; ofs >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, ofs);
+        if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * WARPS + warp) * 8 + 7] = nf;
     }
 #endif
 #undef K1_TRACE
-    if (flagged_counter) {
+    if (o.flagged) {
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 8);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 4);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 2);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 1);
-        if (lane == 0 && nflag) atomicAdd(flagged_counter, (unsigned long long)nflag);
+        if (lane == 0 && nflag) atomicAdd(o.flagged, (unsigned long long)nflag);
+    }
+    if (TC) {
+        tc_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(s_tmem, Cfg::TMEM_COLS);
     }
 }
 

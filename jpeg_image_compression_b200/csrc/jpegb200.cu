@@ -72,12 +72,26 @@ static void canonical(const unsigned char *counts, const unsigned char *values, 
 
 struct HostTables {
     float ref_scale[64], quant_f[64], rk[64];
+    float rk_tc[64];                 // zig-zag order: ref_scale / (Q * 2^21), tensor-core path
+    double tc_weight_sum_err;        // max over coefficients of |sum_i (W_i / 2^21 - w_i)|  
     uint8_t dc_len[16];
     uint32_t dc_code[16], ac_code[256];
-    std::vector<uint8_t> block;      // device table block, TBL_* layout (scan_pack.cuh)
+    std::vector<uint8_t> block;      // device table block, TBL_* layout (common.cuh)
 };
 
 static int bit_length(int v) { int a = v < 0 ? -v : v, n = 0; while (a) { ++n; a >>= 1; } return n; }
+
+// fp16 bit pattern of an integer |v| <= 2048 (exactly representable)
+static uint16_t half_of_int(int v)
+{
+    if (v == 0) return 0;
+    const uint16_t sign = v < 0 ? 0x8000u : 0u;
+    const unsigned a = (unsigned)(v < 0 ? -v : v);
+    int e = 0;
+    while ((a >> (e + 1)) != 0) ++e;                                 // floor(log2 a) <= 11
+    const unsigned mant = e <= 10 ? (a << (10 - e)) & 0x3FFu : (a >> (e - 10)) & 0x3FFu;
+    return (uint16_t)(sign | ((unsigned)(e + 15) << 10) | mant);
+}
 
 static void build_tables(HostTables &t)
 {
@@ -101,20 +115,9 @@ static void build_tables(HostTables &t)
     }
     for (int i = 0; i < 256; ++i) t.ac_code[i] = ((uint32_t)ac[i].code << 8) | ac[i].len;
     t.block.assign(TBL_BYTES, 0);
-    // bit cost of an AC coefficient with int8 value b after `run` zeros: ZRLs + code + amplitude bits
-    for (int run = 0; run < ACLUT_ROWS; ++run) {
-        for (int b = 1; b < 256; ++b) {
-            const int sz = bit_length((int)(int8_t)b);
-            if (sz > 10) continue;
-            t.block[TBL_ACLUT + run * ACLUT_STRIDE + b] =
-                (uint8_t)((run >> 4) * ac[0xF0].len + ac[((run & 15) << 4) | sz].len + sz);
-        }
-    }
-    t.block[TBL_ACLUT + ACLUT_ROWS * ACLUT_STRIDE] = ac[0x00].len;          // EOB
-    // ready-made AC symbols for K2: [run 0..15][int8 value] -> (code << size | amplitude) << 5 | length
-    // (rle.c:24-35,106-113 + huffman.c:39,164-173).  Value 0 never occurs as a coefficient, so slot
-    // [0][0] carries EOB and the unreachable slot [0][0xF0] (-16 at run 0 is a real value: use its
-    // own entry below) is NOT reused: ZRL lives in [0][0x80] (-128 cannot occur, |q| <= 95).
+    // ready-made AC symbols: [run 0..15][int8 value] -> (code << size | amplitude) left-aligned | length in the low
+    // 5 bits (rle.c:24-35,106-113 + huffman.c:39,164-173).  Value 0 never occurs as a coefficient, so slot
+    // [0][0] carries EOB; ZRL lives in [0][0x80] (-128 cannot occur, |q| <= 95).
     {
         uint32_t *sym = reinterpret_cast<uint32_t *>(&t.block[TBL_SYM]);
         for (int run = 0; run < 16; ++run) {
@@ -130,9 +133,37 @@ static void build_tables(HostTables &t)
         sym[0] = ((uint32_t)ac[0x00].code << (32 - ac[0x00].len)) | ac[0x00].len;      // EOB
         sym[0x80] = ((uint32_t)ac[0xF0].code << (32 - ac[0xF0].len)) | ac[0xF0].len;   // ZRL
     }
-    memcpy(&t.block[TBL_AC_CODE], t.ac_code, sizeof(t.ac_code));
     memcpy(&t.block[TBL_DC_CODE], t.dc_code, sizeof(t.dc_code));
-    memcpy(&t.block[TBL_DC_LEN], t.dc_len, sizeof(t.dc_len));
+    // Tensor-core transform: B[n][k], n = (zig-zag position, limb), k = 8 * pixel row + pixel column.
+    // Weight = the reference's own LUT product cos[r][u] * cos[c][v] (dct.c:79-84, exact in double) in 22-bit fixed
+    // point, W = round(w * 2^21) = l0 * 2^11 + l1 with balanced 11-bit limbs: integers that fp16 holds exactly.
+    // Column order inside a zig-zag word (4 positions a b c d): S0(a) S0(b) S1(a) S1(b) S0(c) S0(d) S1(c) S1(d), so that a
+    // lane's tcgen05.ld delivers packed-fp32 operand pairs.  Memory layout = UMMA K-major, no swizzle:
+    // [k/16][n/8][(k%16)/8][n%8][k%8] halves (core matrix = 8 rows x 16 bytes; LBO 128, SBO 256, 4 KB per K step).
+    {
+        uint16_t *bm = reinterpret_cast<uint16_t *>(&t.block[TBL_BMAT]);
+        t.tc_weight_sum_err = 0.0;
+        for (int k = 0; k < 64; ++k) {
+            const int zpos = kZigzag[k], u = zpos >> 3, v = zpos & 7;
+            t.rk_tc[k] = (float)((double)t.ref_scale[zpos] / ((double)std_luminance_quant_tbl[zpos] * 2097152.0));
+            double sum_err = 0.0;
+            for (int r = 0; r < 8; ++r) {
+                for (int c = 0; c < 8; ++c) {
+                    const double w = (double)kRefCos[r * 8 + u] * (double)kRefCos[c * 8 + v];
+                    const long long W = llround(w * 2097152.0);
+                    long long l1 = ((W + 1024) % 2048 + 2048) % 2048 - 1024;         // [-1024, 1023]
+                    long long l0 = (W - l1) / 2048;                                   // [-1024, 1024]
+                    sum_err += (double)W / 2097152.0 - w;
+                    const int kidx = r * 8 + c, ks = kidx / 16, kc = (kidx % 16) / 8, ke = kidx % 8;
+                    for (int limb = 0; limb < 2; ++limb) {
+                        const int n = 8 * (k >> 2) + 4 * ((k & 3) >> 1) + 2 * limb + (k & 1);
+                        bm[ks * 2048 + (n / 8) * 128 + kc * 64 + (n % 8) * 8 + ke] = half_of_int((int)(limb ? l1 : l0));
+                    }
+                }
+            }
+            if (k > 0) t.tc_weight_sum_err = std::max(t.tc_weight_sum_err, std::fabs(sum_err));
+        }
+    }
 }
 
 // ---- encoder handle ---------------------------------------------------------------
@@ -167,7 +198,10 @@ struct jpegb200_encoder {
     int dct_mode = 0;
     int bytes_per_block = 24;
     jb::HostTables tables;
-    jb::DeviceBuffer coef, blkinfo, strips, strip_bits, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace, trace1;
+    jb::DeviceBuffer coef, blkinfo, streams, strips, strip_bits, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace, trace1;
+    uint32_t slot_bytes = 768;      // strip stream slot: 32 blocks x bytes_per_block
+    bool want_taps = false;         // K1 also stores the stage taps (coefficients, per-block bit offsets)
+    bool taps_valid = false;        // ... and did so in the last launch
     // last launch
     jb::PackArgs args{};
     jb::Geom geom{};
@@ -175,6 +209,7 @@ struct jpegb200_encoder {
     uint64_t total_blocks = 0;      // blocks K1 produced (all images, incl. stripe halo)
     uint64_t launches = 0;
     int k2_ctas_per_sm[2] = {0, 0};
+    int k1_grid = 0, k1_warps = 0;   // shape of the last K1 launch
     bool stripe_ready = false;
     // optional per-kernel timing (cudaEvents on the launching stream)
     bool profiling = false;
@@ -200,15 +235,17 @@ static int upload_tables(jpegb200_encoder *enc)
             JB_CUDA(cudaMemcpyToSymbol(c_ref_scale, t.ref_scale, sizeof(t.ref_scale)));
             JB_CUDA(cudaMemcpyToSymbol(c_quant_f, t.quant_f, sizeof(t.quant_f)));
             JB_CUDA(cudaMemcpyToSymbol(c_rk, t.rk, sizeof(t.rk)));
+            JB_CUDA(cudaMemcpyToSymbol(c_rk_tc, t.rk_tc, sizeof(t.rk_tc)));
             JB_CUDA(cudaMemcpyToSymbol(c_zigzag, kZigzag, sizeof(kZigzag)));
             JB_CUDA(cudaMemcpyToSymbol(c_dc_len, t.dc_len, sizeof(t.dc_len)));
             JB_CUDA(cudaMemcpyToSymbol(c_dc_code, t.dc_code, sizeof(t.dc_code)));
             JB_CUDA(cudaMemcpyToSymbol(c_ac_code, t.ac_code, sizeof(t.ac_code)));
-            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_scan_pack_stuff<K2_SMALL_BLOCK_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         k2_smem(K2_SMALL_BLOCK_BITS)));
-            JB_CUDA(cudaFuncSetAttribute(k_scan_pack_stuff<K2_MAX_BLOCK_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         k2_smem(K2_MAX_BLOCK_BITS)));
+            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<true, false>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<true, true>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<false, false>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<false, true>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_merge_stuff<K2_SMALL_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem(K2_SMALL_SLOT)));
+            JB_CUDA(cudaFuncSetAttribute(k_merge_stuff<K2_BIG_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem(K2_BIG_SLOT)));
             g_tables_uploaded[enc->device & 63] = true;
         }
     }
@@ -262,15 +299,21 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
         g_last_error = "launch too large: split the batch (strip index is 32-bit)";
         return JPEGB200_ERR_ARG;
     }
-    const uint64_t nb_avail = g.blocks_per_image, tb = nb_avail * (uint64_t)count;
+    const uint64_t tb = g.blocks_per_image * (uint64_t)count;
     const uint32_t strips_avail = (uint32_t)g.spr * (uint32_t)g.bh;
     const uint32_t strips_owned = (uint32_t)g.spr * (uint32_t)((h + 7) / 8);
     const uint64_t nb_owned = (uint64_t)g.bw * (uint64_t)((h + 7) / 8);
     enc->total_blocks = tb;
-    const int tiles = (int)((strips_owned + K2_WARPS - 1) / K2_WARPS);
+    const int tiles = (int)((strips_owned + K2_TILE_STRIPS - 1) / K2_TILE_STRIPS);
     int rc = 0;
-    if ((rc = enc->coef.reserve(tb * 64))) return rc;
-    if ((rc = enc->blkinfo.reserve(tb * 4))) return rc;
+    // strip stream slots: 32 blocks x bytes_per_block (the hint), at most the per-strip worst case
+    enc->slot_bytes = (uint32_t)std::min(32 * enc->bytes_per_block, enc->bytes_per_block <= 32 ? STREAM_SMALL_BYTES : STREAM_BIG_BYTES);
+    enc->slot_bytes = (enc->slot_bytes + 15u) & ~15u;
+    if ((rc = enc->streams.reserve(g.total_strips * (uint64_t)enc->slot_bytes + 64))) return rc;
+    if (enc->want_taps) {
+        if ((rc = enc->coef.reserve(tb * 64))) return rc;
+        if ((rc = enc->blkinfo.reserve(tb * 4))) return rc;
+    }
     if ((rc = enc->strips.reserve(g.total_strips * sizeof(StripRec)))) return rc;
     if ((rc = enc->strip_bits.reserve(g.total_strips * 4 + 16))) return rc;
     // grouped look-back state of K2 (aggregate per tile + inclusive prefix per 1024-tile group), once
@@ -288,8 +331,8 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
 
     PackArgs &a = enc->args;
     a.tables = static_cast<const uint8_t *>(enc->dtables.ptr);
-    a.coef = static_cast<const int8_t *>(enc->coef.ptr);
-    a.blkinfo = static_cast<const uint32_t *>(enc->blkinfo.ptr);
+    a.streams = static_cast<const uint8_t *>(enc->streams.ptr);
+    a.slot_bytes = enc->slot_bytes;
     a.strips = static_cast<const StripRec *>(enc->strips.ptr);
     a.strip_bits = static_cast<const uint32_t *>(enc->strip_bits.ptr);
     a.bit_incl = static_cast<uint64_t *>(enc->lookback.ptr);
@@ -305,13 +348,11 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.err = misc_err(enc);
     a.strips_owned = strips_owned;
     a.strips_avail = strips_avail;
-    a.spr = (uint32_t)g.spr;
-    a.bw = (uint32_t)g.bw;
-    a.nb_avail = (uint32_t)nb_avail;
     a.tiles = tiles;
     a.count = count;
     a.dc_pred0 = 0;
     a.bit_phase = 0;
+    a.dyn = nullptr;
     a.trace = nullptr;
     if (getenv("JPEGB200_K2_TRACE")) {              // tuning aid: per-tile phase timestamps
         if ((rc = enc->trace.reserve((uint64_t)tiles * count * 64))) return rc;
@@ -378,57 +419,85 @@ static bool make_tensor_map(const Geom &g, CUtensorMap *tm)
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// K1: fused block kernel, persistent, K1_CTAS_PER_SM CTAs per SM
-static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st)
+// transform selection: dct_mode 0 = tensor-core DCT (default), 1 = every coefficient in reference order,
+// 2 = register butterfly DCT (round-1 transform, kept for comparison); JPEGB200_DCT=butterfly forces 2 for mode 0
+static bool use_tensor_dct(const jpegb200_encoder *enc)
 {
-    Geom &g = enc->geom;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    g.use_tmap = make_tensor_map(g, &tmap) ? 1 : 0;
-    const uint64_t want = (g.total_strips + K1_WARPS - 1) / K1_WARPS;
-    int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * K1_CTAS_PER_SM);
+    static const bool env_butterfly = []() { const char *e = getenv("JPEGB200_DCT"); return e && !strcmp(e, "butterfly"); }();
+    return enc->dct_mode == 2 ? false : !env_butterfly;
+}
+
+template <bool TC, bool BIG>
+static int launch_block_kernel_t(jpegb200_encoder *enc, cudaStream_t st, const CUtensorMap &tmap, bool taps, bool stats)
+{
+    using Cfg = K1Cfg<TC, BIG>;
+    const Geom &g = enc->geom;
+    const uint64_t units = TC ? (g.total_strips + 3) / 4 : g.total_strips;            // 4-strip tiles / strips
+    const uint64_t per_cta = TC ? Cfg::GROUPS : Cfg::WARPS;
+    const uint64_t want = (units + per_cta - 1) / per_cta;
+    int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * Cfg::CTAS_PER_SM);
     if (const char *e = getenv("JPEGB200_K1_GRID")) grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, atoi(e)));   // tuning aid
+    enc->k1_grid = grid;
+    enc->k1_warps = Cfg::WARPS;
     if (getenv("JPEGB200_K1_TRACE")) {              // tuning aid: per-warp timestamps
-        if (int rc = enc->trace1.reserve((uint64_t)grid * K1_WARPS * 128)) return rc;     // [warps][8] phases, [warps][8] strip ends
-        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * K1_WARPS * 128, st));
+        if (int rc = enc->trace1.reserve((uint64_t)grid * Cfg::WARPS * 128)) return rc;     // [warps][8] phases, [warps][8] strip ends
+        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * Cfg::WARPS * 128, st));
     }
+    K1Out o;
+    o.strips = static_cast<StripRec *>(enc->strips.ptr);
+    o.strip_bits = static_cast<uint32_t *>(enc->strip_bits.ptr);
+    o.streams = static_cast<uint8_t *>(enc->streams.ptr);
+    o.slot_bytes = enc->slot_bytes;
+    o.dbg_coef = taps ? static_cast<int8_t *>(enc->coef.ptr) : nullptr;
+    o.dbg_blkinfo = taps ? static_cast<uint32_t *>(enc->blkinfo.ptr) : nullptr;
+    o.flagged = stats ? misc_flagged(enc) : nullptr;     // a tap re-run must not count twice
+    o.err = misc_err(enc);
     {
         TimedLaunch t(enc, st, KID_BLOCK);
-        k_fused_blocks<<<grid, K1_THREADS, K1_SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr),
-                                                           static_cast<uint32_t *>(enc->blkinfo.ptr),
-                                                           static_cast<StripRec *>(enc->strips.ptr),
-                                                           static_cast<uint32_t *>(enc->strip_bits.ptr),
-                                                           static_cast<const uint8_t *>(enc->dtables.ptr), misc_flagged(enc),
-                                                           enc->dct_mode, static_cast<uint64_t *>(enc->lookback.ptr),
-                                                           enc->lookback_words, static_cast<unsigned long long *>(enc->trace1.ptr), tmap);
+        k_fused_blocks<TC, BIG><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, o, static_cast<const uint8_t *>(enc->dtables.ptr),
+                                                                        enc->dct_mode == 1 ? 1 : 0, static_cast<uint64_t *>(enc->lookback.ptr),
+                                                                        enc->lookback_words, static_cast<unsigned long long *>(enc->trace1.ptr), tmap);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
 }
 
-// K2: fused scan + pack + stuff over tiles of 8 strips; one CTA per tile if that is a single wave,
-// otherwise as many persistent CTAs as can be co-resident, drawing tiles by ticket
+// K1: fused block kernel, persistent
+static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st, bool stats = true)
+{
+    Geom &g = enc->geom;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    g.use_tmap = make_tensor_map(g, &tmap) ? 1 : 0;
+    const bool taps = enc->want_taps;
+    enc->taps_valid = taps;
+    const bool big = enc->slot_bytes > (uint32_t)STREAM_SMALL_BYTES;
+    if (use_tensor_dct(enc))
+        return big ? launch_block_kernel_t<true, true>(enc, st, tmap, taps, stats) : launch_block_kernel_t<true, false>(enc, st, tmap, taps, stats);
+    return big ? launch_block_kernel_t<false, true>(enc, st, tmap, taps, stats) : launch_block_kernel_t<false, false>(enc, st, tmap, taps, stats);
+}
+
+// K2: scan + shift-merge + stuff over tiles of 8 strips; as many CTAs as can be co-resident (at most one per tile),
+// drawing tiles by ticket
 static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {
     const PackArgs &a = enc->args;
-    // window size: 32 bytes per block on average over a tile unless the caller asked for more workspace
-    const bool small = enc->bytes_per_block * 8 <= K2_SMALL_BLOCK_BITS;
-    const int smem = small ? k2_smem(K2_SMALL_BLOCK_BITS) : k2_smem(K2_MAX_BLOCK_BITS);
+    const bool small = enc->slot_bytes <= (uint32_t)K2_SMALL_SLOT;
+    const int smem = small ? k2_smem(K2_SMALL_SLOT) : k2_smem(K2_BIG_SLOT);
     int &per_sm = enc->k2_ctas_per_sm[small ? 0 : 1];
     if (per_sm == 0) {
         int n = 0;
-        if (small) JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan_pack_stuff<K2_SMALL_BLOCK_BITS>, K2_THREADS, smem));
-        else JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan_pack_stuff<K2_MAX_BLOCK_BITS>, K2_THREADS, smem));
+        if (small) JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff<K2_SMALL_SLOT>, K2_THREADS, smem));
+        else JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff<K2_BIG_SLOT>, K2_THREADS, smem));
         per_sm = n > 0 ? n : 1;
     }
     const uint64_t total = (uint64_t)a.tiles * (uint64_t)a.count;
     unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);
     if (const char *e = getenv("JPEGB200_K2_GRID")) grid = std::max(1u, std::min(grid, (unsigned)atoi(e)));   // tuning aid
-    enc->args.dynamic_tiles = total > grid ? 1 : 0;            // more tiles than one wave: persistent CTAs + ticket counter
     {
         TimedLaunch t(enc, st, KID_ENTROPY);
-        if (small) k_scan_pack_stuff<K2_SMALL_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
-        else k_scan_pack_stuff<K2_MAX_BLOCK_BITS><<<grid, K2_THREADS, smem, st>>>(a);
+        if (small) k_merge_stuff<K2_SMALL_SLOT><<<grid, K2_THREADS, smem, st>>>(a);
+        else k_merge_stuff<K2_BIG_SLOT><<<grid, K2_THREADS, smem, st>>>(a);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -490,6 +559,33 @@ static int encode_launch(jpegb200_encoder *enc, uint8_t *d_scan, uint64_t scan_c
     return JPEGB200_OK;
 }
 
+// Stage taps (zig-zag coefficients, per-block bit offsets) are not part of the production data flow any more: K1
+// keeps the coefficients on chip.  The tap readers re-run K1 on the last launch's geometry with the taps enabled
+// (the input must still be resident), unless that launch already stored them.
+static int ensure_taps(jpegb200_encoder *enc)
+{
+    JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    if (enc->taps_valid) return JPEGB200_OK;
+    if (!enc->geom.rgb || enc->total_blocks == 0) {
+        g_last_error = "no previous launch";
+        return JPEGB200_ERR_ARG;
+    }
+    int rc = 0;
+    if ((rc = enc->coef.reserve(enc->total_blocks * 64))) return rc;
+    if ((rc = enc->blkinfo.reserve(enc->total_blocks * 4))) return rc;
+    const bool keep = enc->want_taps;
+    const uint64_t launches = enc->launches;
+    enc->want_taps = true;
+    rc = launch_block_kernel(enc, nullptr, /*stats=*/false);
+    enc->want_taps = keep;
+    enc->launches = launches;
+    if (rc) return rc;
+    JB_CUDA(cudaDeviceSynchronize());
+    enc->taps_valid = true;
+    return JPEGB200_OK;
+}
+
 }  // namespace jb
 
 using namespace jb;
@@ -535,7 +631,7 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
     cudaSetDevice(enc->device);
     cudaDeviceSynchronize();
     harvest_events(enc);
-    for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
+    for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->streams, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
                             &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace, &enc->trace1})
         b->release();
     delete enc;
@@ -543,7 +639,7 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
 
 extern "C" int jpegb200_encoder_set_dct_mode(jpegb200_encoder *enc, int dct_mode)
 {
-    if (!enc || (dct_mode != 0 && dct_mode != 1)) return JPEGB200_ERR_ARG;
+    if (!enc || dct_mode < 0 || dct_mode > 2) return JPEGB200_ERR_ARG;
     enc->dct_mode = dct_mode;
     return JPEGB200_OK;
 }
@@ -643,8 +739,7 @@ extern "C" int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out
 extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, uint64_t nblocks)
 {
     if (!enc || !host_zz || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
-    JB_CUDA(cudaSetDevice(enc->device));
-    JB_CUDA(cudaDeviceSynchronize());
+    if (int rc = ensure_taps(enc)) return rc;
     std::vector<int8_t> tmp((size_t)nblocks * 64);
     JB_CUDA(cudaMemcpy(tmp.data(), enc->coef.ptr, tmp.size(), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < tmp.size(); ++i) host_zz[i] = tmp[i];
@@ -675,19 +770,20 @@ extern "C" int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host
 extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t *host_bits, uint64_t nblocks)
 {
     if (!enc || !host_bits || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
-    JB_CUDA(cudaSetDevice(enc->device));
-    JB_CUDA(cudaDeviceSynchronize());
+    if (int rc = ensure_taps(enc)) return rc;
     const PackArgs &a = enc->args;
+    const uint32_t spr = (uint32_t)enc->geom.spr, bw = (uint32_t)enc->geom.bw;
+    const uint64_t nb_avail = enc->geom.blocks_per_image;
     std::vector<uint32_t> info((size_t)enc->total_blocks);
     std::vector<StripRec> recs((size_t)a.strips_avail * a.count);
-    JB_CUDA(cudaMemcpy(info.data(), a.blkinfo, info.size() * 4, cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpy(info.data(), enc->blkinfo.ptr, info.size() * 4, cudaMemcpyDeviceToHost));
     JB_CUDA(cudaMemcpy(recs.data(), a.strips, recs.size() * sizeof(StripRec), cudaMemcpyDeviceToHost));
     uint64_t done = 0;
     for (int img = 0; img < a.count && done < nblocks; ++img) {
         for (uint32_t s = 0; s < a.strips_avail && done < nblocks; ++s) {
-            const uint32_t brow = s / a.spr, sx = s % a.spr;
-            const uint32_t vb = std::min<uint32_t>(32u, a.bw - sx * 32u);
-            const uint64_t b0 = (uint64_t)img * a.nb_avail + (uint64_t)brow * a.bw + sx * 32u;
+            const uint32_t brow = s / spr, sx = s % spr;
+            const uint32_t vb = std::min<uint32_t>(32u, bw - sx * 32u);
+            const uint64_t b0 = (uint64_t)img * nb_avail + (uint64_t)brow * bw + sx * 32u;
             const StripRec &r = recs[(size_t)img * a.strips_avail + s];
             // only the image's first DC symbol is not in K1's counts (its predictor is a run-time argument)
             const uint32_t fix = s == 0 ? enc->tables.dc_len[bit_length((int)r.first_dc - (int)a.dc_pred0)] : 0u;
@@ -903,7 +999,9 @@ extern "C" JpegEncoderBuffer *jpegb200_encode_scan_dbg(const BMPImage *image, in
         JpegEncoderBuffer *result = (JpegEncoderBuffer *)malloc(sizeof(JpegEncoderBuffer));
         uint64_t n = 0;
         int rc = JPEGB200_ERR_INTERNAL;
+        enc->want_taps = first_block != nullptr;      // the orchestrator prints the first block's coefficients
         if (host && result) rc = jpegb200_encode_host(enc, image->data, image->width, image->height, host, cap, &n, nullptr);
+        enc->want_taps = false;
         if (rc == JPEGB200_OK) {
             if (first_block) {
                 int8_t zz[64];

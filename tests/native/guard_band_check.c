@@ -7,7 +7,13 @@
  *   max of |s_ref - g*T| / (kGammaA*A + kGammaC*Ac + kGamma0)             (must stay below 1)
  * with A = sum|p|, Ac = sum|p - round(mean p)| -- the two guard half-widths used on the device --
  * for several input families.
- * usage: guard_band_check <nblocks> <seed> <kGammaA> <kGammaC> <kGamma0>
+ * usage: guard_band_check <nblocks> <seed> <kGammaA> <kGammaC> <kGamma0> [tc]
+ *
+ * With "tc" the fast value is the tensor-core transform's instead: the reference's LUT products in 22-bit fixed
+ * point, W = round(cos[r][u]*cos[c][v] * 2^21) = l0*2^11 + l1, integer limb sums S0 = sum p*l0, S1 = sum p*l1 (exact on
+ * the device: fp16 integer operands, fp32 accumulation of integers below 2^24) and t = fmaf(S0, 2048, S1); the ratios
+ * are those of |s_ref - t/2^21|.  A third number is printed: max over AC coefficients of |sum_i (W_i/2^21 - w_i)| in
+ * units of u = 2^-24 (it enters the A-term of the refined bound).
  */
 #include <math.h>
 #include <stdint.h>
@@ -55,6 +61,24 @@ int main(int argc, char **argv)
     rng_state = argc > 2 ? (uint64_t)atoll(argv[2]) : 1;
     const double g[8] = {1.0, 1.0, cos(M_PI / 8), 1.0, cos(M_PI / 4), 1.0, cos(M_PI / 8), 1.0};
     double worst = 0.0, worst2 = 0.0;
+    const int tc = argc > 6;
+    static long long l0[64][64], l1[64][64];        /* [u*8+v][r*8+c] */
+    double max_sum_err = 0.0;
+    for (int u = 0; u < 8; ++u)
+        for (int v = 0; v < 8; ++v) {
+            double se = 0.0;
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c) {
+                    const double w = (double)k_cos[r][u] * (double)k_cos[c][v];
+                    const long long W = llround(w * 2097152.0);
+                    const long long lo = ((W + 1024) % 2048 + 2048) % 2048 - 1024;
+                    l1[u * 8 + v][r * 8 + c] = lo;
+                    l0[u * 8 + v][r * 8 + c] = (W - lo) / 2048;
+                    if (llabs(lo) > 1024 || llabs((W - lo) / 2048) > 1024) { fprintf(stderr, "limb out of range\n"); return 2; }
+                    se += (double)W / 2097152.0 - w;
+                }
+            if ((u || v) && fabs(se) > max_sum_err) max_sum_err = fabs(se);
+        }
     const double gA = argc > 3 ? atof(argv[3]) : 1.0431e-6, gC = argc > 4 ? atof(argv[4]) : 6.1394e-6, g0 = argc > 5 ? atof(argv[5]) : 2.9803e-5;
     for (long n = 0; n < nblocks; ++n) {
         int p[8][8];
@@ -97,11 +121,23 @@ int main(int argc, char **argv)
                         acc = acc + t;
                     }
                 if (u == 0 && v == 0) continue;             /* DC is handled exactly on the device */
-                const double diff = fabs((double)acc - g[u] * g[v] * (double)x[u][v]);
+                double fast = g[u] * g[v] * (double)x[u][v];
+                if (tc) {
+                    long long S0 = 0, S1 = 0;
+                    for (int r = 0; r < 8; ++r)
+                        for (int c = 0; c < 8; ++c) {
+                            S0 += (long long)p[r][c] * l0[u * 8 + v][r * 8 + c];
+                            S1 += (long long)p[r][c] * l1[u * 8 + v][r * 8 + c];
+                        }
+                    if (llabs(S0) >= (1 << 24) || llabs(S1) >= (1 << 24)) { fprintf(stderr, "limb sum not exact in fp32\n"); return 2; }
+                    fast = (double)fmaf((float)S0, 2048.0f, (float)S1) / 2097152.0;
+                }
+                const double diff = fabs((double)acc - fast);
                 if (diff / A > worst) worst = diff / A;
                 if (diff / (gA * A + gC * Ac + g0) > worst2) worst2 = diff / (gA * A + gC * Ac + g0);
             }
     }
-    printf("%.6e %.6e\n", worst, worst2);
+    if (tc) printf("%.6e %.6e %.3f\n", worst, worst2, max_sum_err * 16777216.0);
+    else printf("%.6e %.6e\n", worst, worst2);
     return 0;
 }
