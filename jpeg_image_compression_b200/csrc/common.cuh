@@ -152,6 +152,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// 4-bit mask of the non-zero bytes of a word (bit j <-> byte j)
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
+{
+    const uint32_t t = (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;   // 0x80 per non-zero byte
+    return (t * 0x00204081u) >> 28;                                             // gather bits 7,15,23,31
+}
+
 // ---- tcgen05 / tensor memory (5th-generation tensor cores) ---------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t columns)      // one whole warp
 {

@@ -2,8 +2,7 @@
 //
 // One pass over the RGB payload: luma (converter.c:51) + edge replication (converter.c:31,36) + level shift
 // (converter.c:84-86) + 8x8 forward DCT (dct.c:63-96) + quantization (quantization.c:34-36) + zig-zag
-// (zigzag.c:51-60) + DC-difference / run-length symbols (rle.c:51-127) + Huffman codes and amplitude bits
-// (huffman.c:121-193) -- every coefficient is walked ONCE, here, and leaves the kernel as entropy-coded bits.
+// (zigzag.c:51-60).  Output: the quantized coefficients as int8 in zig-zag order, 64 bytes per block.
 //
 // Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels, 6 KB of RGB).  One warp owns
 // a strip, one lane a block:
@@ -24,11 +23,9 @@
 //      TC = false: scaled even/odd butterfly in registers (rows scalar, columns packed fp32), as in round 1.
 //      In both cases the value is bracketed (see below) and the few coefficients whose bracket straddles a rounding
 //      boundary are re-evaluated in the reference's exact operation order;
-//   4. entropy coding of the strip: non-zero map of the lane's block, bit cost by a walk over the non-zero
-//      coefficients only, warp scan -> bit offset of every block inside the strip, second walk emitting the Huffman
-//      code + amplitude bits of every symbol into the strip's bit window in shared memory (one table look-up per
-//      symbol), and the window goes to the strip's slot in global memory with 128-bit stores.  K2 only shifts the
-//      strips' streams to their global bit phase and stuffs.
+//   4. 4 x 128-bit stores of the block's 64 coefficient bytes.
+// The entropy stage is a kernel of its own (strip_entropy.cuh): its sparse symbol walks are latency-bound and want
+// two to three times the occupancy this register-heavy kernel can have (measured: DESIGN.md section 3).
 //
 // Bit-exactness.  The reference sums 64 products sequentially in fp32 with two unfused multiplies per term;
 // replaying that costs ~136 flop/pixel.  Instead the fast value is bracketed: |s_ref - fast| <= gamma(A, Ac) with
@@ -49,30 +46,21 @@ constexpr int RAW_PITCH = 784;                       // 768 payload + 16 bytes o
 constexpr int RAW_BYTES = 8 * RAW_PITCH;             // 6272
 constexpr int Y_PITCH = 256;
 constexpr int Y_BYTES = 8 * Y_PITCH;                 // 2048
-constexpr int HALO_BYTES = 256;                      // the raster-predecessor block's 8 x 24 RGB bytes (192), padded
 constexpr int TMAP_ROW_BYTES = 768;                  // a tensor-map box is dense: 8 rows x 768 bytes
-constexpr int K1_SYM_BYTES = 16384;                  // AC symbol table staged in shared memory
 constexpr int K1_BMAT_BYTES = 16384;                 // limb matrix of the tensor-core transform
-constexpr int STREAM_SMALL_BYTES = 1024;             // strip stream capacity of the default instantiation (32 B/block)
-constexpr int STREAM_BIG_BYTES = 5888;               // worst case: 32 blocks x 1463 bits = 5852 bytes
 
-// Launch shape and shared-memory carve-up of the four instantiations.
-//   TC:      one CTA per SM, warps in groups of four (a 128-block MMA tile); TMEM: 160 columns per group
-//   BIGWIN:  strip streams up to 184 bytes per block (any input); fewer warps fit
-template <bool TC, bool BIGWIN>
+// Launch shape and shared-memory carve-up of the two instantiations.
+//   TC: one CTA per SM, warps in groups of four (a 128-block MMA tile); TMEM: 160 columns per group, 3 groups fit
+template <bool TC>
 struct K1Cfg {
-    static constexpr int WARPS = TC ? (BIGWIN ? 8 : 12) : 8;
+    static constexpr int WARPS = TC ? 12 : 8;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int CTAS_PER_SM = (TC || BIGWIN) ? 1 : 2;
+    static constexpr int CTAS_PER_SM = TC ? 1 : 2;
     static constexpr int GROUPS = WARPS / 4;
-    static constexpr int STREAM_BYTES = BIGWIN ? STREAM_BIG_BYTES : STREAM_SMALL_BYTES;
-    static constexpr int WIN_BYTES = STREAM_BYTES + 128;             // + slack: the bit writer may touch one word past the end
-    static constexpr int ZS_PITCH = (TC || BIGWIN) ? 20 : 17;        // words per lane of the coefficient staging area
-    static constexpr int ZS_BYTES = 32 * ZS_PITCH * 4;
-    static constexpr int WARP_SMEM = RAW_BYTES + Y_BYTES + ZS_BYTES + HALO_BYTES + WIN_BYTES;
-    static constexpr int TABLE_BYTES = K1_SYM_BYTES + (TC ? K1_BMAT_BYTES : 0);
+    static constexpr int WARP_SMEM = RAW_BYTES + Y_BYTES;             // 8320 = 65 x 128
+    static constexpr int TABLE_BYTES = TC ? K1_BMAT_BYTES : 0;
     static constexpr int SMEM = TABLE_BYTES + WARPS * WARP_SMEM;
-    static constexpr int TMEM_COLS = GROUPS == 3 ? 512 : 256;        // 160 per group, power of two
+    static constexpr int TMEM_COLS = 512;                            // 160 per group, power of two
     static_assert(WARP_SMEM % 128 == 0, "per-warp region must keep the tensor-map tiles 128-byte aligned");
 };
 constexpr int TC_GROUP_COLS = 160;                   // 128 accumulator columns (2 limbs x 64) + 32 columns of A
@@ -92,9 +80,6 @@ struct StripCtx {
     int vb;                  // 8x8 blocks in the strip (<= 32)
     uint32_t mispack;        // 16-byte phase of each of the 8 row pointers, 4 bits per row
     int tx, ty, tz;          // tensor-map coordinates of the tile: word column, pixel row, image
-    // the block that precedes the strip in raster order (its DC is the strip's first predictor)
-    const uint8_t *halo;     // its top-left pixel; nullptr for the first strip of an image
-    int halo_rmax, halo_cmax;// last real row / column inside that block (edges replicate)
 };
 
 // position of a strip: image, block row, strip inside the block row.  Found by division once per warp and
@@ -142,19 +127,6 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
     c.tx = (int)(sx * 192u);
     c.ty = (int)(brow * 8u);
     c.tz = (int)img;
-    if (sx > 0) {                                   // previous block is in the same block row
-        c.halo = c.row0 - 24;
-        c.halo_rmax = c.rmax;
-        c.halo_cmax = 7;
-    } else if (brow > 0) {                          // last block of the previous block row
-        const int hx0 = (g.bw - 1) * 8;
-        c.halo = c.row0 - 8 * c.pitch + (int64_t)hx0 * 3;
-        c.halo_rmax = 7;
-        c.halo_cmax = g.w - 1 - hx0;
-    } else {
-        c.halo = nullptr;
-        c.halo_rmax = c.halo_cmax = 0;
-    }
     return c;
 }
 
@@ -162,8 +134,7 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
 // through the warp's mbarrier.  Each row copy starts at the row's 16-byte-aligned address and covers whole 16-byte
 // chunks, so any width / base alignment works.  Also records the rows' 16-byte phases in c.mispack.  Must be called
 // by the whole warp.
-__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint8_t *hal, uint64_t *bar, int lane,
-                                                  const CUtensorMap *tmap)
+__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane, const CUtensorMap *tmap)
 {
     if (tmap) {
         // aligned input: ONE tensor-map copy of the 8 x 768-byte box (rows and columns beyond the image are
@@ -174,13 +145,6 @@ __device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uin
             mbar_expect_tx(bar, 8 * TMAP_ROW_BYTES);
             tensor_g2s_3d(raw, tmap, c.tx, c.ty, c.tz, bar);
         }
-        // the raster-predecessor block (8 rows x 24 bytes, 8-byte aligned here) rides along as 24 asynchronous
-        // 8-byte copies whose completion is folded into the same mbarrier phase (every lane arrives once)
-        if (c.halo != nullptr && lane < 24) {
-            const int r = lane / 3, part = lane - 3 * r;
-            cp_async8(hal + lane * 8, c.halo + (int64_t)min(r, c.halo_rmax) * c.pitch + 8 * part);
-        }
-        cp_async_mbar_arrive_noinc(bar);
         return;
     }
     const int r = lane & 7;
@@ -332,153 +296,13 @@ __device__ __forceinline__ void dct8_2(f32x2 &x0, f32x2 &x1, f32x2 &x2, f32x2 &x
 // scale class of a frequency index: 0 -> g=1, 1 -> g=cos(pi/8), 2 -> g=cos(pi/4)
 __host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 : (k == 4 ? 2 : 0); }
 
-// ---- entropy coding helpers ------------------------------------------------------------------------------
-
-__device__ __forceinline__ int magnitude_class(int v)          // rle.c:9-22
+template <bool TC>
+__global__ void __launch_bounds__(K1Cfg<TC>::THREADS, K1Cfg<TC>::CTAS_PER_SM)
+k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restrict__ tables, unsigned long long *__restrict__ flagged_counter,
+               const int exact_mode, uint64_t *__restrict__ lookback_state, const uint64_t lookback_words,
+               unsigned long long *__restrict__ trace, const __grid_constant__ CUtensorMap tmap_param)
 {
-    const int a = v < 0 ? -v : v;
-    return 32 - __clz(a);
-}
-
-// shared-memory accesses by 32-bit shared-space address: keeps the symbol loops free of the
-// generic-to-shared address arithmetic the compiler otherwise repeats at every access
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v, bool enable)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p red.shared.or.b32 [%0], %1;\n}"
-                 :: "r"(saddr), "r"(v), "r"((uint32_t)enable) : "memory");
-}
-
-// MSB-first bit appender with a 32-bit register accumulator, flushed word-wise into the zeroed
-// shared-memory window with OR-reductions (the first and last word of a block are shared with its
-// neighbours).  Branch-free: the flush is predicated.
-struct BitWriter {
-    uint32_t waddr;       // shared-space address of the window word being filled
-    uint32_t acc, fill;
-    __device__ __forceinline__ void start(uint32_t win_saddr, uint32_t relbit)
-    {
-        waddr = win_saddr + ((relbit >> 5) << 2);
-        fill = relbit & 31u;
-        acc = 0;
-    }
-    __device__ __forceinline__ void put(uint32_t vl, uint32_t n)           // n in 1..27 bits, left-aligned in vl
-    {
-        acc |= vl >> fill;
-        fill += n;
-        const bool full = fill >= 32u;
-        red_or_shared(waddr, acc, full);
-        fill &= 31u;
-        waddr += full ? 4u : 0u;
-        acc = full ? vl << (n - fill) : acc;                               // the bits that did not fit (none if fill == 0)
-    }
-    __device__ __forceinline__ void finish() { red_or_shared(waddr, acc, fill != 0u); }
-};
-
-// 4-bit mask of the non-zero bytes of a word (bit j <-> byte j)
-__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
-{
-    const uint32_t t = (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;   // 0x80 per non-zero byte
-    return (t * 0x00204081u) >> 28;                                             // gather bits 7,15,23,31
-}
-
-// Bit cost of a block's AC symbols (rle.c:83-123 with the code lengths of huffman.c:89-104): the lane visits only
-// the non-zero coefficients (map mlo/mhi, bit k <-> zig-zag position k); each visit is one look-up in the symbol
-// table sym[run & 15][value & 255], whose low 5 bits are the symbol's length (code + amplitude bits).
-// zs: shared-space address of the block's 64 coefficient bytes.  Returns the bits; `last` = position of the last non-zero.
-__device__ __forceinline__ uint32_t ac_cost(uint32_t zs, uint32_t mlo, uint32_t mhi, uint32_t sym, uint32_t zrl_len,
-                                            uint32_t eob_len, int &last)
-{
-    uint32_t bits = 0;
-    int prev = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t m = half ? mhi : mlo;
-#pragma unroll 1
-        while (m) {
-            const int k = 32 * half + __ffs((int)m) - 1;
-            m &= m - 1;
-            const uint32_t byte = lds_u8(zs + (uint32_t)k);
-            const uint32_t run = (uint32_t)(k - prev - 1);
-            prev = k;
-            bits += (run >> 4) * zrl_len + (lds_u32(sym + 4u * (((run & 15u) << 8) | byte)) & 31u);   // ZRLs: rle.c:99-103
-        }
-    }
-    last = prev;
-    if (prev < 63) bits += eob_len;                                                   // EOB, rle.c:121-123
-    return bits;
-}
-
-// Emit one block's symbols (rle.c:59-124 -> huffman.c:145-173) through the bit writer.  sym[run][value] holds
-// (Huffman code << size | amplitude bits) left-aligned with the total length in the low 5 bits, i.e. huffman.c:164-173
-// applied to the symbol rle.c:106-113 would have produced; slot [0][0] carries EOB and [0][0x80] ZRL.
-__device__ __forceinline__ void emit_block(BitWriter &bw, uint32_t zs, bool with_dc, int diff, uint32_t dc_entry, uint32_t mlo,
-                                           uint32_t mhi, uint32_t sym)
-{
-    if (with_dc) {                                                                    // rle.c:68-76
-        const int sz = magnitude_class(diff);
-        const uint32_t amp = (uint32_t)(diff > 0 ? diff : diff - 1) & ((1u << sz) - 1u);   // rle.c:24-35, huffman.c:39
-        const uint32_t n = (dc_entry & 0xFFu) + (uint32_t)sz;
-        bw.put((((dc_entry >> 8) << sz) | amp) << (32u - n), n);
-    }
-    int prev = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t m = half ? mhi : mlo;
-#pragma unroll 1
-        while (m) {
-            const int k = 32 * half + __ffs((int)m) - 1;
-            m &= m - 1;
-            const uint32_t byte = lds_u8(zs + (uint32_t)k);
-            int run = k - prev - 1;
-            prev = k;
-            if (run >= 16) {                                                           // ZRL, rle.c:99-103
-                const uint32_t z = lds_u32(sym + 4u * 0x80u);
-                do {
-                    bw.put(z & ~31u, z & 31u);
-                    run -= 16;
-                } while (run >= 16);
-            }
-            const uint32_t e = lds_u32(sym + 4u * (((uint32_t)run << 8) | byte));
-            bw.put(e & ~31u, e & 31u);
-        }
-    }
-    if (prev < 63) {                                                                   // EOB, rle.c:121-123
-        const uint32_t e = lds_u32(sym);
-        bw.put(e & ~31u, e & 31u);
-    }
-    bw.finish();
-}
-
-// what K1 leaves behind
-struct K1Out {
-    StripRec *strips;              // [total_strips]
-    uint32_t *strip_bits;          // [total_strips] compact copy of StripRec.bits
-    uint8_t *streams;              // [total_strips][slot_bytes]: the strip's bits, MSB first in 32-bit words
-    uint32_t slot_bytes;           // multiple of 16, <= the instantiation's STREAM_BYTES
-    int8_t *dbg_coef;              // optional stage tap: [blocks][64] zig-zag int8
-    uint32_t *dbg_blkinfo;         // optional stage tap: bit offset inside the strip | last non-zero << 16
-    unsigned long long *flagged;   // coefficients re-evaluated in reference order (statistics)
-    uint32_t *err;
-};
-
-template <bool TC, bool BIGWIN>
-__global__ void __launch_bounds__(K1Cfg<TC, BIGWIN>::THREADS, K1Cfg<TC, BIGWIN>::CTAS_PER_SM)
-k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, const int exact_mode,
-               uint64_t *__restrict__ lookback_state, const uint64_t lookback_words, unsigned long long *__restrict__ trace,
-               const __grid_constant__ CUtensorMap tmap_param)
-{
-    using Cfg = K1Cfg<TC, BIGWIN>;
+    using Cfg = K1Cfg<TC>;
     constexpr int WARPS = Cfg::WARPS;
 #ifdef JPEGB200_TRACE   // tracing build only (make trace -> libjpegb200_trace.so)
 #define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
@@ -491,15 +315,6 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
     const CUtensorMap *tmap = g.use_tmap ? &tmap_param : nullptr;
     const uint32_t raw_pitch = g.use_tmap ? TMAP_ROW_BYTES : RAW_PITCH;
     uint8_t *ybuf = raw + RAW_BYTES;
-    uint32_t *zs = reinterpret_cast<uint32_t *>(ybuf + Y_BYTES) + lane * Cfg::ZS_PITCH;   // this lane's 64 coefficient bytes
-    uint8_t *hal = ybuf + Y_BYTES + Cfg::ZS_BYTES;               // predecessor block, tensor-map path only
-    uint32_t *win = reinterpret_cast<uint32_t *>(hal + HALO_BYTES);   // the strip's bit window
-    uint32_t smem_sa = smem_u32(smem);
-    asm volatile("mov.b32 %0, %0;" : "+r"(smem_sa));             // opaque: computed once, not rematerialised at every use
-    const uint32_t sym_sa = smem_sa;                             // symbol table at offset 0
-    const uint32_t zs_sa = smem_sa + (uint32_t)(reinterpret_cast<uint8_t *>(zs) - smem);
-    const uint32_t win_sa = smem_sa + (uint32_t)(reinterpret_cast<uint8_t *>(win) - smem);
-    __shared__ uint32_t s_dc[16];                                // DC codes: (code << 8) | len per size class
     __shared__ __align__(8) uint64_t s_bar[WARPS + 1 + 3];       // per-warp tile barriers, the table barrier, per-group MMA barriers
     __shared__ uint32_t s_tmem;
 
@@ -513,13 +328,12 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
     uint32_t tile_s0 = TC ? (s & ~3u) : s;                       // group-uniform loop variable
     uint64_t *bar = &s_bar[warp];
     uint64_t *table_bar = &s_bar[WARPS];
-    if (lane == 0) mbar_init(bar, g.use_tmap ? 33 : 1);          // tensor-map path: + one asynchronous arrival per lane
+    if (lane == 0) mbar_init(bar, 1);
     if (threadIdx.x == 0) {
         mbar_init(table_bar, 1);
         if (TC)
             for (int i = 0; i < Cfg::GROUPS; ++i) mbar_init(&s_bar[WARPS + 1 + i], 1);
     }
-    if (threadIdx.x < 16) s_dc[threadIdx.x] = reinterpret_cast<const uint32_t *>(tables + TBL_DC_CODE)[threadIdx.x];
     mbar_fence_init();
     if (TC && warp == 0) tmem_alloc(&s_tmem, Cfg::TMEM_COLS);
     if (TC) tc_fence_before_sync();
@@ -532,19 +346,17 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
     if (s < total) {
         pos = strip_pos(g, s);
         cur = strip_ctx(g, pos);
-        strip_issue_loads(cur, raw, hal, bar, lane, tmap);                  // first strip's pixels are in flight ...
+        strip_issue_loads(cur, raw, bar, lane, tmap);                  // first strip's pixels are in flight ...
     }
-    if (threadIdx.x == 0) {                                      // ... while the tables are staged (TMA bulk copies)
-        mbar_expect_tx(table_bar, Cfg::TABLE_BYTES);
-        bulk_g2s(smem, tables + TBL_SYM, K1_SYM_BYTES, table_bar);
-        if (TC) bulk_g2s(smem + K1_SYM_BYTES, tables + TBL_BMAT, K1_BMAT_BYTES, table_bar);
+    if (TC && threadIdx.x == 0) {                                // ... while the limb matrix is staged (one 16 KB TMA bulk copy)
+        mbar_expect_tx(table_bar, K1_BMAT_BYTES);
+        bulk_g2s(smem, tables + TBL_BMAT, K1_BMAT_BYTES, table_bar);
     }
-    // reset the look-back state of the entropy kernel (K2) that follows in the stream: keeps a
-    // whole encode at two launches and CUDA-graph replayable
+    // reset the look-back state of the merge kernel (K2) that follows in the stream: keeps a
+    // whole encode CUDA-graph replayable without a memset node
     for (uint64_t i = (uint64_t)blockIdx.x * Cfg::THREADS + threadIdx.x; i < lookback_words;
          i += (uint64_t)gridDim.x * Cfg::THREADS)
         lookback_state[i] = 0;
-    bool table_ready = false;                                    // waited for at its first use
     K1_TRACE(1);
 
     // tensor memory of this warp's group: accumulators at column 160 * group, A at + 128; the warp owns lanes 32 * (warp % 4)
@@ -557,35 +369,19 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
 
     uint32_t nflag = 0;
     const uint32_t xforce = exact_mode ? 0x01010101u : 0u;
-    const uint32_t cap_bits = o.slot_bytes * 8u;
     float magic;                                     // 1.5 * 2^23 held in a register: leaves the FFMA's
     asm("mov.f32 %0, 0f4B400000;" : "=f"(magic));     // constant-bank slot to the quantizer constant
 
     for (; tile_s0 < total; tile_s0 += stride, s += stride) {
         const bool valid = s < total;                            // TC: the last tile may have idle warps
-        uint32_t halo_y = 0;
         StripCtx me = cur;
         uint32_t yw[16];                                         // the lane's 64 luma bytes (TC)
         uint32_t absdev = 0, absmean = 0;                        // A = sum |Y - 128|, Ac = sum |Y - mean|
         float x00 = 0.0f;                                        // sum (Y - 128), exact
         if (valid) {
-            // luma sum of the raster-predecessor block: lane l covers row l/4, columns 2*(l%4) and +1;
-            // the loads are issued now and consumed after the transform
-            if (cur.halo && !tmap) {
-                const uint8_t *hp = cur.halo + (int64_t)min(lane >> 2, cur.halo_rmax) * cur.pitch;
-                const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
-                const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
-                halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
-            }
             mbar_wait(bar, phase);
             phase ^= 1u;
-            if (cur.halo && tmap) {                          // same sum from the block staged in shared memory
-                const uint8_t *hp = hal + 24 * (lane >> 2);
-                const uint8_t *p0 = hp + 3 * min(2 * (lane & 3), cur.halo_cmax), *p1 = hp + 3 * min(2 * (lane & 3) + 1, cur.halo_cmax);
-                const uint32_t k0 = g.wt_lo & 0xFFu, k1 = (g.wt_lo >> 8) & 0xFFu, k2 = (g.wt_lo >> 16) & 0xFFu;
-                halo_y = ((k0 * p0[0] + k1 * p0[1] + k2 * p0[2]) >> 8) + ((k0 * p1[0] + k1 * p1[1] + k2 * p1[2]) >> 8);
-            }
-            if (!table_ready) K1_TRACE(2);
+            K1_TRACE(2);
 
             // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
             if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
@@ -620,7 +416,7 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
             if (s + stride < total) {
                 strip_advance(g, pos, dq, dr);
                 cur = strip_ctx(g, pos);
-                strip_issue_loads(cur, raw, hal, bar, lane, tmap);
+                strip_issue_loads(cur, raw, bar, lane, tmap);
             }
 
             // right-edge replication inside the last real block (converter.c:36)
@@ -670,9 +466,9 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
             tc_fence_before_sync();
             named_bar_sync(1 + group, 128);                      // the tile's four A quarters are in tensor memory
             if (quad == 0 && lane == 0) {
-                if (!table_ready) mbar_wait(table_bar, 0);
+                mbar_wait(table_bar, 0);                       // the limb matrix (immediate after the first tile)
                 tc_fence_after_sync();
-                const uint32_t b_sa = smem_sa + K1_SYM_BYTES;
+                const uint32_t b_sa = smem_u32(smem);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)                   // K = 64 in four steps of 16; B: 4 KB per step, LBO 128, SBO 256
                     umma_f16_ts(tmem_d, tmem_a + 8u * ks, umma_desc(b_sa + 4096u * ks, 128u, 256u), TC_IDESC, ks > 0 ? 1u : 0u);
@@ -787,8 +583,6 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
         }
         if (!valid) continue;                                    // (TC only) idle warp of the last tile: barriers done
 
-        uint32_t my_bits = 0, mlo = 0, mhi = 0;                  // this lane's block: bit cost, non-zero map of its AC coefficients
-        int my_last = 0, my_dc = 0;
         if (lane < me.vb) {
             // DC: exact integer sum in all formulations; reference operation sequence
             // fl(k00 * S) / 16 then roundf (dct.c:93, quantization.c:36)
@@ -797,7 +591,6 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
                 const int dcq = (int)roundf(f * 0.0625f);
                 zw[0] = (zw[0] & 0xFFFFFF00u) | ((uint32_t)dcq & 0xFFu);
                 xw[0] &= 0xFFFFFF00u;
-                my_dc = dcq;
             }
             uint32_t anyx = 0;
 #pragma unroll
@@ -824,93 +617,11 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
                     ++nflag;
                 }
             }
-            // park the coefficient bytes in shared memory (the symbol walks index them by position) and build the
-            // 63-bit map of the non-zero AC coefficients
-            if (Cfg::ZS_PITCH % 4 == 0) {
+            uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 64);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4 *>(zs)[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
-            } else {
-#pragma unroll
-                for (int w = 0; w < 16; ++w) zs[w] = zw[w];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t m16 = nonzero_nibble(zw[4 * i]) | (nonzero_nibble(zw[4 * i + 1]) << 4) | (nonzero_nibble(zw[4 * i + 2]) << 8) |
-                                     (nonzero_nibble(zw[4 * i + 3]) << 12);
-                if (i < 2) mlo |= m16 << (16 * i);
-                else mhi |= m16 << (16 * (i - 2));
-            }
-            mlo &= ~1u;                                          // position 0 is the DC
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
         }
-        if (!table_ready) {
-            K1_TRACE(3);
-            mbar_wait(table_bar, 0);                             // the symbol table, staged during the first transform
-            table_ready = true;
-            K1_TRACE(4);
-        }
-        __syncwarp();
-        if (lane < me.vb) {
-            const uint32_t zrl = lds_u32(sym_sa + 4u * 0x80u) & 31u, eob = lds_u32(sym_sa) & 31u;
-            my_bits = ac_cost(zs_sa, mlo, mhi, sym_sa, zrl, eob, my_last);
-        }
-        // DC differences (rle.c:68-76).  The strip's first block is predicted from the block before the strip, whose
-        // quantized DC follows from its 64 luma values alone (an exact integer sum, same closed form as above).  The
-        // very first block of an image is coded by K2 (its predictor is 0, or the previous stripe's last DC in
-        // multi-GPU runs).
-        int diff;
-        bool with_dc;
-        uint32_t dc_entry = 0;
-        {
-#pragma unroll
-            for (int ofs = 16; ofs > 0; ofs >>= 1) halo_y += __shfl_xor_sync(0xffffffffu, halo_y, ofs);
-            int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
-            if (lane == 0) {
-                const float f = __fmul_rn(c_ref_scale[0], (float)((int)halo_y - 8192));
-                prev_dc = (int)roundf(f * 0.0625f);
-            }
-            diff = my_dc - prev_dc;
-            with_dc = lane < me.vb && (lane > 0 || me.halo);
-            if (with_dc) {
-                const int sz = magnitude_class(diff);
-                dc_entry = s_dc[sz];
-                my_bits += (dc_entry & 0xFFu) + (uint32_t)sz;
-            }
-        }
-        uint32_t incl = my_bits;
-#pragma unroll
-        for (int ofs = 1; ofs < 32; ofs <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, ofs);
-            if (lane >= ofs) incl += n;
-        }
-        const uint32_t strip_total = __shfl_sync(0xffffffffu, incl, 31);
-        const bool fits = strip_total <= cap_bits;
-        const uint32_t nquads = fits ? (strip_total + 127u) >> 7 : 0u;               // 16-byte units written to the slot
-        // ---- emit the strip's bits into the zeroed window, then window -> the strip's slot ------------------------
-        for (uint32_t i = lane; i < nquads + 1; i += 32) reinterpret_cast<uint4 *>(win)[i] = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
-        if (fits && lane < me.vb) {
-            BitWriter bw;
-            bw.start(win_sa, incl - my_bits);
-            emit_block(bw, zs_sa, with_dc, diff, dc_entry, mlo, mhi, sym_sa);
-        }
-        __syncwarp();
-        {
-            uint4 *dst = reinterpret_cast<uint4 *>(o.streams + (uint64_t)s * o.slot_bytes);
-            for (uint32_t i = lane; i < nquads; i += 32) dst[i] = reinterpret_cast<const uint4 *>(win)[i];
-            const int first_dc = __shfl_sync(0xffffffffu, my_dc, 0);
-            if (lane == me.vb - 1) {
-                o.strips[s] = StripRec{strip_total, (int16_t)first_dc, (int16_t)my_dc};
-                o.strip_bits[s] = strip_total;
-                if (!fits) atomicOr(o.err, ERRBIT_WORKSPACE);
-            }
-            if (o.dbg_coef && lane < me.vb) {                    // stage taps for the parity tests
-                uint4 *cd = reinterpret_cast<uint4 *>(o.dbg_coef + (me.block0 + (uint32_t)lane) * 64);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) cd[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
-                o.dbg_blkinfo[me.block0 + (uint32_t)lane] = (incl - my_bits) | ((uint32_t)my_last << 16);
-            }
-        }
-        __syncwarp();
+        __syncwarp();                                            // the Y tile is rewritten by the next strip's luma pass
 #ifdef JPEGB200_TRACE
         // second half of the trace buffer: completion times of this warp's first 8 strips
         if (trace && lane == 0) {
@@ -930,13 +641,13 @@ k_fused_blocks(const Geom g, const K1Out o, const uint8_t *__restrict__ tables, 
     }
 #endif
 #undef K1_TRACE
-    if (o.flagged) {
+    if (flagged_counter) {
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 8);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 4);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 2);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 1);
-        if (lane == 0 && nflag) atomicAdd(o.flagged, (unsigned long long)nflag);
+        if (lane == 0 && nflag) atomicAdd(flagged_counter, (unsigned long long)nflag);
     }
     if (TC) {
         tc_fence_before_sync();

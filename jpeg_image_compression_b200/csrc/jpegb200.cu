@@ -20,6 +20,7 @@
 #include "scan_pack.cuh"
 #include "entropy.cuh"
 #include "fused_block.cuh"
+#include "strip_entropy.cuh"
 #include "stages.cuh"
 #include "synth.cuh"
 
@@ -240,12 +241,11 @@ static int upload_tables(jpegb200_encoder *enc)
             JB_CUDA(cudaMemcpyToSymbol(c_dc_len, t.dc_len, sizeof(t.dc_len)));
             JB_CUDA(cudaMemcpyToSymbol(c_dc_code, t.dc_code, sizeof(t.dc_code)));
             JB_CUDA(cudaMemcpyToSymbol(c_ac_code, t.ac_code, sizeof(t.ac_code)));
-            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<true, false>::SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<true, true>::SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<false, false>::SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<false, true>::SMEM));
-            JB_CUDA(cudaFuncSetAttribute(k_merge_stuff<K2_SMALL_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem(K2_SMALL_SLOT)));
-            JB_CUDA(cudaFuncSetAttribute(k_merge_stuff<K2_BIG_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem(K2_BIG_SLOT)));
+            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<true>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_fused_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<false>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_strip_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1bCfg<false>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_strip_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1bCfg<true>::SMEM));
+            JB_CUDA(cudaFuncSetAttribute(k_merge_stuff, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem(STREAM_BIG_BYTES)));
             g_tables_uploaded[enc->device & 63] = true;
         }
     }
@@ -310,10 +310,8 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     enc->slot_bytes = (uint32_t)std::min(32 * enc->bytes_per_block, enc->bytes_per_block <= 32 ? STREAM_SMALL_BYTES : STREAM_BIG_BYTES);
     enc->slot_bytes = (enc->slot_bytes + 15u) & ~15u;
     if ((rc = enc->streams.reserve(g.total_strips * (uint64_t)enc->slot_bytes + 64))) return rc;
-    if (enc->want_taps) {
-        if ((rc = enc->coef.reserve(tb * 64))) return rc;
-        if ((rc = enc->blkinfo.reserve(tb * 4))) return rc;
-    }
+    if ((rc = enc->coef.reserve(tb * 64))) return rc;
+    if (enc->want_taps && (rc = enc->blkinfo.reserve(tb * 4))) return rc;
     if ((rc = enc->strips.reserve(g.total_strips * sizeof(StripRec)))) return rc;
     if ((rc = enc->strip_bits.reserve(g.total_strips * 4 + 16))) return rc;
     // grouped look-back state of K2 (aggregate per tile + inclusive prefix per 1024-tile group), once
@@ -363,7 +361,7 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
 
 // ---- kernel launches (optionally bracketed by cudaEvents for per-kernel timing) -----------
 
-enum KernelId { KID_BLOCK = 0, KID_ENTROPY = 1, KID_LAYOUT = 2, KID_COMPACT = 3, KID_FRAME = 4 };
+enum KernelId { KID_BLOCK = 0, KID_ENTROPY = 1, KID_LAYOUT = 2, KID_COMPACT = 3, KID_FRAME = 4, KID_STRIP = 5 };
 
 struct TimedLaunch {
     jpegb200_encoder *enc;
@@ -427,10 +425,10 @@ static bool use_tensor_dct(const jpegb200_encoder *enc)
     return enc->dct_mode == 2 ? false : !env_butterfly;
 }
 
-template <bool TC, bool BIG>
-static int launch_block_kernel_t(jpegb200_encoder *enc, cudaStream_t st, const CUtensorMap &tmap, bool taps, bool stats)
+template <bool TC>
+static int launch_block_kernel_t(jpegb200_encoder *enc, cudaStream_t st, const CUtensorMap &tmap, bool stats)
 {
-    using Cfg = K1Cfg<TC, BIG>;
+    using Cfg = K1Cfg<TC>;
     const Geom &g = enc->geom;
     const uint64_t units = TC ? (g.total_strips + 3) / 4 : g.total_strips;            // 4-strip tiles / strips
     const uint64_t per_cta = TC ? Cfg::GROUPS : Cfg::WARPS;
@@ -443,38 +441,58 @@ static int launch_block_kernel_t(jpegb200_encoder *enc, cudaStream_t st, const C
         if (int rc = enc->trace1.reserve((uint64_t)grid * Cfg::WARPS * 128)) return rc;     // [warps][8] phases, [warps][8] strip ends
         JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * Cfg::WARPS * 128, st));
     }
-    K1Out o;
-    o.strips = static_cast<StripRec *>(enc->strips.ptr);
-    o.strip_bits = static_cast<uint32_t *>(enc->strip_bits.ptr);
-    o.streams = static_cast<uint8_t *>(enc->streams.ptr);
-    o.slot_bytes = enc->slot_bytes;
-    o.dbg_coef = taps ? static_cast<int8_t *>(enc->coef.ptr) : nullptr;
-    o.dbg_blkinfo = taps ? static_cast<uint32_t *>(enc->blkinfo.ptr) : nullptr;
-    o.flagged = stats ? misc_flagged(enc) : nullptr;     // a tap re-run must not count twice
-    o.err = misc_err(enc);
     {
         TimedLaunch t(enc, st, KID_BLOCK);
-        k_fused_blocks<TC, BIG><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, o, static_cast<const uint8_t *>(enc->dtables.ptr),
-                                                                        enc->dct_mode == 1 ? 1 : 0, static_cast<uint64_t *>(enc->lookback.ptr),
-                                                                        enc->lookback_words, static_cast<unsigned long long *>(enc->trace1.ptr), tmap);
+        k_fused_blocks<TC><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr), static_cast<const uint8_t *>(enc->dtables.ptr),
+                                                                   stats ? misc_flagged(enc) : nullptr, enc->dct_mode == 1 ? 1 : 0,
+                                                                   static_cast<uint64_t *>(enc->lookback.ptr), enc->lookback_words,
+                                                                   static_cast<unsigned long long *>(enc->trace1.ptr), tmap);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
 }
 
-// K1: fused block kernel, persistent
+// K1: fused block kernel (persistent) -> int8 zig-zag coefficients
 static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st, bool stats = true)
 {
     Geom &g = enc->geom;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     g.use_tmap = make_tensor_map(g, &tmap) ? 1 : 0;
-    const bool taps = enc->want_taps;
+    return use_tensor_dct(enc) ? launch_block_kernel_t<true>(enc, st, tmap, stats) : launch_block_kernel_t<false>(enc, st, tmap, stats);
+}
+
+// K1b: strip entropy kernel (persistent) -> strip bit streams + strip records
+static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool taps)
+{
+    const Geom &g = enc->geom;
+    StripArgs sa;
+    sa.coef = static_cast<const int8_t *>(enc->coef.ptr);
+    sa.tables = static_cast<const uint8_t *>(enc->dtables.ptr);
+    sa.strips = static_cast<StripRec *>(enc->strips.ptr);
+    sa.strip_bits = static_cast<uint32_t *>(enc->strip_bits.ptr);
+    sa.streams = static_cast<uint8_t *>(enc->streams.ptr);
+    sa.slot_bytes = enc->slot_bytes;
+    sa.dbg_blkinfo = taps ? static_cast<uint32_t *>(enc->blkinfo.ptr) : nullptr;
+    sa.err = misc_err(enc);
+    sa.total_strips = (uint32_t)g.total_strips;
+    sa.spr = (uint32_t)g.spr;
+    sa.bw = (uint32_t)g.bw;
+    sa.bh = (uint32_t)g.bh;
+    sa.blocks_per_image = g.blocks_per_image;
     enc->taps_valid = taps;
     const bool big = enc->slot_bytes > (uint32_t)STREAM_SMALL_BYTES;
-    if (use_tensor_dct(enc))
-        return big ? launch_block_kernel_t<true, true>(enc, st, tmap, taps, stats) : launch_block_kernel_t<true, false>(enc, st, tmap, taps, stats);
-    return big ? launch_block_kernel_t<false, true>(enc, st, tmap, taps, stats) : launch_block_kernel_t<false, false>(enc, st, tmap, taps, stats);
+    const uint64_t want = (g.total_strips + 7) / 8;
+    const int per_sm = big ? K1bCfg<true>::CTAS_PER_SM : K1bCfg<false>::CTAS_PER_SM;
+    int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * per_sm);
+    if (const char *e = getenv("JPEGB200_K1B_GRID")) grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, atoi(e)));   // tuning aid
+    {
+        TimedLaunch t(enc, st, KID_STRIP);
+        if (big) k_strip_entropy<true><<<grid, K1bCfg<true>::THREADS, K1bCfg<true>::SMEM, st>>>(sa);
+        else k_strip_entropy<false><<<grid, K1bCfg<false>::THREADS, K1bCfg<false>::SMEM, st>>>(sa);
+    }
+    JB_CUDA(cudaGetLastError());
+    return JPEGB200_OK;
 }
 
 // K2: scan + shift-merge + stuff over tiles of 8 strips; as many CTAs as can be co-resident (at most one per tile),
@@ -482,13 +500,12 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st, bool stat
 static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {
     const PackArgs &a = enc->args;
-    const bool small = enc->slot_bytes <= (uint32_t)K2_SMALL_SLOT;
-    const int smem = small ? k2_smem(K2_SMALL_SLOT) : k2_smem(K2_BIG_SLOT);
+    const int smem = k2_smem((int)enc->slot_bytes), win_words = k2_win_words((int)enc->slot_bytes);
+    const bool small = enc->slot_bytes <= (uint32_t)STREAM_SMALL_BYTES;
     int &per_sm = enc->k2_ctas_per_sm[small ? 0 : 1];
     if (per_sm == 0) {
-        int n = 0;
-        if (small) JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff<K2_SMALL_SLOT>, K2_THREADS, smem));
-        else JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff<K2_BIG_SLOT>, K2_THREADS, smem));
+        int n = 0;         // occupancy at the largest window of the class
+        JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff, K2_THREADS, k2_smem(small ? STREAM_SMALL_BYTES : STREAM_BIG_BYTES)));
         per_sm = n > 0 ? n : 1;
     }
     const uint64_t total = (uint64_t)a.tiles * (uint64_t)a.count;
@@ -496,8 +513,7 @@ static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
     if (const char *e = getenv("JPEGB200_K2_GRID")) grid = std::max(1u, std::min(grid, (unsigned)atoi(e)));   // tuning aid
     {
         TimedLaunch t(enc, st, KID_ENTROPY);
-        if (small) k_merge_stuff<K2_SMALL_SLOT><<<grid, K2_THREADS, smem, st>>>(a);
-        else k_merge_stuff<K2_BIG_SLOT><<<grid, K2_THREADS, smem, st>>>(a);
+        k_merge_stuff<<<grid, K2_THREADS, smem, st>>>(a, win_words);
     }
     JB_CUDA(cudaGetLastError());
     return JPEGB200_OK;
@@ -534,6 +550,7 @@ static int encode_launch(jpegb200_encoder *enc, uint8_t *d_scan, uint64_t scan_c
         a.out_capacity = scan_capacity > extra ? scan_capacity - extra : 0;
     }
     if ((rc = launch_block_kernel(enc, st))) return rc;
+    if ((rc = launch_strip_entropy(enc, st, enc->want_taps))) return rc;
     if ((rc = launch_entropy(enc, st))) return rc;
     if (a.count > 1) {
         {
@@ -567,22 +584,17 @@ static int ensure_taps(jpegb200_encoder *enc)
     JB_CUDA(cudaSetDevice(enc->device));
     JB_CUDA(cudaDeviceSynchronize());
     if (enc->taps_valid) return JPEGB200_OK;
-    if (!enc->geom.rgb || enc->total_blocks == 0) {
+    if (!enc->coef.ptr || enc->total_blocks == 0) {
         g_last_error = "no previous launch";
         return JPEGB200_ERR_ARG;
     }
     int rc = 0;
-    if ((rc = enc->coef.reserve(enc->total_blocks * 64))) return rc;
     if ((rc = enc->blkinfo.reserve(enc->total_blocks * 4))) return rc;
-    const bool keep = enc->want_taps;
     const uint64_t launches = enc->launches;
-    enc->want_taps = true;
-    rc = launch_block_kernel(enc, nullptr, /*stats=*/false);
-    enc->want_taps = keep;
+    rc = launch_strip_entropy(enc, nullptr, /*taps=*/true);      // same coefficients, same streams, plus the per-block offsets
     enc->launches = launches;
     if (rc) return rc;
     JB_CUDA(cudaDeviceSynchronize());
-    enc->taps_valid = true;
     return JPEGB200_OK;
 }
 
@@ -739,7 +751,8 @@ extern "C" int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out
 extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, uint64_t nblocks)
 {
     if (!enc || !host_zz || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
-    if (int rc = ensure_taps(enc)) return rc;
+    JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
     std::vector<int8_t> tmp((size_t)nblocks * 64);
     JB_CUDA(cudaMemcpy(tmp.data(), enc->coef.ptr, tmp.size(), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < tmp.size(); ++i) host_zz[i] = tmp[i];
@@ -808,6 +821,7 @@ extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_r
     if (rc) return rc;
     enc->launches = 0;
     if ((rc = launch_block_kernel(enc, st))) return rc;
+    if ((rc = launch_strip_entropy(enc, st, enc->want_taps))) return rc;
     const PackArgs &a = enc->args;
     std::vector<StripRec> recs(a.strips_owned);
     JB_CUDA(cudaMemcpyAsync(recs.data(), a.strips, recs.size() * sizeof(StripRec), cudaMemcpyDeviceToHost, st));
@@ -999,9 +1013,7 @@ extern "C" JpegEncoderBuffer *jpegb200_encode_scan_dbg(const BMPImage *image, in
         JpegEncoderBuffer *result = (JpegEncoderBuffer *)malloc(sizeof(JpegEncoderBuffer));
         uint64_t n = 0;
         int rc = JPEGB200_ERR_INTERNAL;
-        enc->want_taps = first_block != nullptr;      // the orchestrator prints the first block's coefficients
         if (host && result) rc = jpegb200_encode_host(enc, image->data, image->width, image->height, host, cap, &n, nullptr);
-        enc->want_taps = false;
         if (rc == JPEGB200_OK) {
             if (first_block) {
                 int8_t zz[64];

@@ -30,14 +30,14 @@
 
 namespace jb {
 
-constexpr int K2_WARPS = 8;
+constexpr int K2_WARPS = 4;
 constexpr int K2_THREADS = K2_WARPS * 32;
-constexpr int K2_TILE_STRIPS = 8;                              // strips per tile
-constexpr int K2_SEGS = K2_TILE_STRIPS + 3;                    // + the image's first DC symbol + two successor strips
-constexpr int K2_SMALL_SLOT = 1024;                            // strip slot sizes of the two instantiations
-constexpr int K2_BIG_SLOT = 5888;
-constexpr int k2_win_words(int slot_bytes) { return K2_TILE_STRIPS * slot_bytes / 4 + 8; }
-constexpr int k2_smem(int slot_bytes) { return 2 * k2_win_words(slot_bytes) * 4; }
+constexpr int K2_TILE_STRIPS = 16;                             // strips per tile
+constexpr int K2_SEGS = K2_TILE_STRIPS + 1;                    // + the image's first DC symbol (the successor strips are handled apart)
+constexpr int K2_ROUND_WORDS = 4 * K2_THREADS;                 // write-out: four window words per thread and round
+constexpr int K2_STAGE_BYTES = 2 * 4 * K2_ROUND_WORDS + 32;    // stuffed bytes of one round (worst case: every byte 0xFF) + alignment phase
+__host__ __device__ constexpr int k2_win_words(int slot_bytes) { return K2_TILE_STRIPS * slot_bytes / 4 + 8; }
+__host__ __device__ constexpr int k2_smem(int slot_bytes) { return 2 * k2_win_words(slot_bytes) * 4 + K2_STAGE_BYTES; }
 
 // stripes: values that are only known after the ranks' exchange may be read from device memory (written by
 // k_stripe_resolve), so that analyze -> exchange -> encode needs no host round trip
@@ -133,16 +133,14 @@ struct PendingTile {
     uint32_t tile_ff;    // 0xFF bytes among them
 };
 
-// SLOT_BYTES: capacity of a strip's stream slot.  The default instantiation (1024: 32 bytes per block) keeps
-// shared memory small; an image that needs more raises ERRBIT_WORKSPACE in K1 and the caller re-runs both kernels
-// with the worst-case instantiation, selected through jpegb200_encoder_set_bytes_per_block.
-template <int SLOT_BYTES>
+// The windows are sized at launch (dynamic shared memory): K2_TILE_STRIPS x the strip slot size.  An image that needs
+// bigger slots raises ERRBIT_WORKSPACE in K1 and the caller re-runs both kernels with a larger bytes_per_block.
 __global__ void __launch_bounds__(K2_THREADS)
-k_merge_stuff(const PackArgs a)
+k_merge_stuff(const PackArgs a, const int win_words)
 {
-    constexpr int WIN_WORDS = k2_win_words(SLOT_BYTES);
-    extern __shared__ __align__(16) uint32_t k2_smem_words[];   // two windows
-    __shared__ uint32_t s_seg_end[K2_SEGS + 1];     // inclusive prefix of the segment lengths (bits, relative to the tile's begin)
+    extern __shared__ __align__(16) uint32_t k2_smem_words[];   // two windows, then the output staging area
+    uint8_t *stage = reinterpret_cast<uint8_t *>(k2_smem_words + 2 * win_words);
+    __shared__ uint32_t s_seg_end[32];              // inclusive prefix of the segment lengths (bits, relative to the tile's begin), padded with ~0
     __shared__ uint32_t s_seg_raw[2];               // bit counts of the two strips after the tile
     __shared__ uint32_t s_pseudo[2];                // the image's first DC symbol, left-aligned; its length
     __shared__ uint32_t s_warp[K2_WARPS];
@@ -169,7 +167,7 @@ k_merge_stuff(const PackArgs a)
         mine.t = ~0ull;
         unsigned long long ticket = ~0ull;
         if (have_tile) {
-            uint32_t *win = k2_smem_words + cur * WIN_WORDS;
+            uint32_t *win = k2_smem_words + cur * win_words;
             const int img = a.count == 1 ? 0 : (int)((uint32_t)t / (uint32_t)a.tiles);   // tickets fit 32 bits
             const int tile = (int)((uint32_t)t - (uint32_t)img * (uint32_t)a.tiles);
             const uint64_t strip_base = (uint64_t)img * a.strips_avail;                  // index of the image's strip 0
@@ -181,10 +179,10 @@ k_merge_stuff(const PackArgs a)
 
             K2_TRACE(t, 0);
             // ---- 1. segment table and tile bit offset (wait-free) -------------------------------------------------
-            // segments: 0 = the image's first DC symbol (tile 0 only), 1..nstrips = the tile's strips,
-            // then up to two following strips that complete the tile's last byte
+            // segments: 0 = the image's first DC symbol (tile 0 only), 1..nstrips = the tile's strips; up to two
+            // following strips complete the tile's last byte
             const int g0 = (tile / LB_GROUP) * LB_GROUP;
-            uint32_t part = 0;                                       // a 1024-tile group holds < 2^29 bits
+            uint32_t part = 0;                                       // a 1024-tile group holds < 2^30 bits
             {
                 const uint32_t lo = (uint32_t)g0 * K2_TILE_STRIPS, hi = strip0;
                 const uint32_t head = min(hi, lo + ((4u - (uint32_t)((strip_base + lo) & 3u)) & 3u));   // up to 16-byte alignment
@@ -217,11 +215,11 @@ k_merge_stuff(const PackArgs a)
                 }
                 uint32_t incl = len;
 #pragma unroll
-                for (int o = 1; o < 16; o <<= 1) {
+                for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += n;
                 }
-                if ((uint32_t)lane <= nstrips) s_seg_end[lane] = incl;
+                s_seg_end[lane] = (uint32_t)lane <= nstrips ? incl : 0xFFFFFFFFu;
             }
             if (tid == 0) s_scratch[K2_WARPS] = g0 > 0 ? lb_wait(bit_incl + tile / LB_GROUP - 1, a.err) : (tile > 0 ? fix0 : 0u);
 #pragma unroll
@@ -242,11 +240,10 @@ k_merge_stuff(const PackArgs a)
             // short as 6 bits, so up to two); the image's last tile is zero-padded instead (huffman.c:65-81)
             const uint32_t need = (8u - (uint32_t)(end & 7u)) & 7u;
             const uint32_t succ1 = min(need, s_seg_raw[0]), succ2 = min(need - succ1, s_seg_raw[1]);
-            const uint32_t total_bits = tile_bits + succ1 + succ2;
             const uint64_t w0 = begin >> 5;
             const uint64_t limit = (end + 7) & ~7ull;                // first bit NOT owned by this tile
             uint32_t nwords = (uint32_t)(((limit + 31) >> 5) - w0);  // covers the completed last byte
-            const bool fits = nwords + 2 <= (uint32_t)WIN_WORDS;
+            const bool fits = nwords + 6 <= (uint32_t)win_words;
             if (!fits) {                                              // cannot happen with consistent slot sizes; never overrun
                 if (tid == 0) atomicOr(a.err, ERRBIT_WORKSPACE);
                 nwords = 0;
@@ -256,19 +253,21 @@ k_merge_stuff(const PackArgs a)
             // ---- 2. assemble the tile's words: shift every overlapping segment to the global bit phase ---------------
             {
                 const int rel0 = -(int)(uint32_t)(begin - (w0 << 5));          // tile-relative bit position of window word 0
+                const uint8_t *tile_streams = a.streams + (strip_base + strip0) * (uint64_t)a.slot_bytes;
                 for (uint32_t j = tid; j < nwords; j += K2_THREADS) {
                     const int P = rel0 + 32 * (int)j;                          // this word covers tile bits [P, P + 32)
                     const uint32_t Pc = P > 0 ? (uint32_t)P : 0u;
                     uint32_t acc = 0;
-                    uint32_t k = 0, seg_begin = 0;
-                    // first segment that ends after Pc
-                    while (k <= nstrips && s_seg_end[k] <= Pc) ++k;
-                    if (k > 0) seg_begin = s_seg_end[k - 1];
+                    // first segment that ends after Pc: branch-free binary search in the padded table
+                    uint32_t k = 0;
+#pragma unroll
+                    for (uint32_t step = 16; step > 0; step >>= 1)
+                        if (s_seg_end[k + step - 1] <= Pc) k += step;
+                    uint32_t seg_begin = k > 0 ? s_seg_end[k - 1] : 0u;
                     while (k <= nstrips && (int)seg_begin < P + 32) {
                         const uint32_t seg_end = s_seg_end[k], len = seg_end - seg_begin;
                         if (len) {
-                            const uint32_t *src = k == 0 ? s_pseudo
-                                                         : reinterpret_cast<const uint32_t *>(a.streams + (strip_base + strip0 + k - 1) * (uint64_t)a.slot_bytes);
+                            const uint32_t *src = k == 0 ? s_pseudo : reinterpret_cast<const uint32_t *>(tile_streams + (k - 1) * (uint64_t)a.slot_bytes);
                             acc |= segment_bits(src, P - (int)seg_begin, len);
                         }
                         seg_begin = seg_end;
@@ -276,21 +275,19 @@ k_merge_stuff(const PackArgs a)
                     }
                     // the (at most two) strips after the tile, clipped to the bits that complete the last byte
                     if ((int)tile_bits < P + 32 && succ1) {
-                        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.streams + (strip_base + strip0 + nstrips) * (uint64_t)a.slot_bytes);
-                        acc |= segment_bits(src, P - (int)tile_bits, succ1);
-                        if (succ2) {
-                            const uint32_t *src2 = reinterpret_cast<const uint32_t *>(a.streams + (strip_base + strip0 + nstrips + 1) * (uint64_t)a.slot_bytes);
-                            acc |= segment_bits(src2, P - (int)(tile_bits + succ1), succ2);
-                        }
+                        acc |= segment_bits(reinterpret_cast<const uint32_t *>(tile_streams + nstrips * (uint64_t)a.slot_bytes), P - (int)tile_bits, succ1);
+                        if (succ2)
+                            acc |= segment_bits(reinterpret_cast<const uint32_t *>(tile_streams + (nstrips + 1) * (uint64_t)a.slot_bytes),
+                                                P - (int)(tile_bits + succ1), succ2);
                     }
                     win[j] = acc;
                 }
-                (void)total_bits;
+                if (tid < 4) win[nwords + tid] = 0;                            // the write-out reads whole 16-byte groups
             }
             __syncthreads();
 
             K2_TRACE(t, 4);
-            // ---- 4. count the 0xFF bytes this tile owns and publish the count ---------------------------
+            // ---- 3. count the 0xFF bytes this tile owns and publish the count ---------------------------
             // owned bytes: [B0, B1) of the image's stream; window byte index = stream byte - 4*w0
             mine.t = t;
             mine.w0 = w0;
@@ -314,11 +311,11 @@ k_merge_stuff(const PackArgs a)
             K2_TRACE(t, 5);
         }
 
-        // ---- 5. the previously assembled tile: stuffed-zero look-back, then write its bytes -------------------
+        // ---- 4. the previously assembled tile: stuffed-zero look-back, then write its bytes -------------------
         // (after the last ticket this is an extra round that only writes)
         const PendingTile w = pend;
         if (w.t != ~0ull) {
-            const uint32_t *win = k2_smem_words + (cur ^ 1) * WIN_WORDS;
+            const uint32_t *win = k2_smem_words + (cur ^ 1) * win_words;
             const int img = a.count == 1 ? 0 : (int)((uint32_t)w.t / (uint32_t)a.tiles);
             const int tile = (int)((uint32_t)w.t - (uint32_t)img * (uint32_t)a.tiles);
             uint64_t *ff_incl = a.ff_incl + (uint64_t)img * groups;
@@ -337,18 +334,32 @@ k_merge_stuff(const PackArgs a)
             }
             K2_TRACE(w.t, 6);
             const uint32_t wb0 = (uint32_t)(w.B0 - 4 * w.w0), wb1 = (uint32_t)(w.B1 - 4 * w.w0);
-            const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;
+            const uint32_t wlast = (wb1 + 3) >> 2;
             uint8_t *out = a.out + (uint64_t)img * a.out_slot;
-            const uint64_t out_base = (w.B0 - origin) + ff_excl;      // output index of window byte wb0
-            // two consecutive window words per thread and round: a typical tile (about 340 words) is one round
-            uint32_t carry = 0;                                       // stuffed zeros of the earlier rounds (uniform)
-            for (uint32_t i0 = wfirst; i0 < wlast; i0 += 2 * K2_THREADS) {
-                if (i0 != wfirst) __syncthreads();                    // s_warp is rewritten in every round
-                const uint32_t i = i0 + 2 * tid;
-                const uint32_t v0 = i < wlast ? masked_word(win, i, wb0, wb1) : 0u;
-                const uint32_t v1 = i + 1 < wlast ? masked_word(win, i + 1, wb0, wb1) : 0u;
-                const uint32_t cnt = count_ff_bytes(v0) + count_ff_bytes(v1);
-                uint32_t incl = cnt;
+            uint64_t round_pos = (w.B0 - origin) + ff_excl;           // output index of the round's first byte
+            // Rounds of four consecutive window words (16 stream bytes) per thread.  The stuffed bytes (huffman.c:26-32)
+            // are laid out in the staging area at the output's 16-byte phase and leave as aligned 128-bit stores;
+            // only the ragged first / last 16-byte unit of a round is written byte by byte.
+            for (uint32_t i0 = (wb0 >> 2) & ~3u; i0 < wlast; i0 += K2_ROUND_WORDS) {
+                const uint32_t i = i0 + 4 * tid;
+                uint32_t v[4];
+                {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(win + i);    // beyond wlast: masked off below
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                }
+                // owned bytes of this thread's group: window bytes [lo, hi)
+                const uint32_t lo = min(max(4u * i, wb0), wb1), hi = max(min(4u * i + 16u, wb1), lo);
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t m = v[j];
+                    const uint32_t b = 4u * (i + j);
+                    if (b < lo) m &= lo - b >= 4u ? 0u : 0xFFFFFFFFu >> (8u * (lo - b));
+                    if (b + 4u > hi) m &= hi > b ? 0xFFFFFFFFu << (8u * (b + 4u - hi)) : 0u;
+                    cnt += count_ff_bytes(m);
+                }
+                const uint32_t nb = hi - lo;                                      // owned stream bytes
+                uint32_t incl = (cnt << 16) | nb;                                 // both prefix sums at once (nb, cnt <= 2^15 per round)
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
@@ -356,37 +367,45 @@ k_merge_stuff(const PackArgs a)
                 }
                 if (lane == 31) s_warp[warp] = incl;
                 __syncthreads();
-                uint32_t before = carry + incl - cnt;
-                uint32_t round_total = 0;
+                uint32_t before = incl - ((cnt << 16) | nb), round_total = 0;
 #pragma unroll
                 for (int ww = 0; ww < K2_WARPS; ++ww) {
                     const uint32_t ws = s_warp[ww];
                     if (ww < warp) before += ws;
                     round_total += ws;
                 }
-                carry += round_total;
-                if (i < wlast) {
-                    uint64_t pos = out_base + before + ((uint64_t)i * 4 > wb0 ? (uint64_t)i * 4 - wb0 : 0);
+                const uint32_t round_bytes = (round_total & 0xFFFFu) + (round_total >> 16);   // stuffed bytes of this round
+                const uint32_t phase = (uint32_t)((uintptr_t)(out + round_pos) & 15u);
+                uint32_t rel = phase + (before & 0xFFFFu) + (before >> 16);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        if (i + j < wlast) {
-                            const uint32_t raw = win[i + j];
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t wb = (i + j) * 4 + k;
-                                if (wb >= wb0 && wb < wb1) {
-                                    const uint8_t byte = (uint8_t)(raw >> (24 - 8 * k));
-                                    if (pos < a.out_capacity) out[pos] = byte;
-                                    ++pos;
-                                    if (byte == 0xFF) {                 // huffman.c:29-31
-                                        if (pos < a.out_capacity) out[pos] = 0x00;
-                                        ++pos;
-                                    }
-                                }
-                            }
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t b = 4u * (i + j) + kb;
+                        if (b >= lo && b < hi) {
+                            const uint32_t byte = (v[j] >> (24 - 8 * kb)) & 0xFFu;
+                            stage[rel++] = (uint8_t)byte;
+                            if (byte == 0xFFu) stage[rel++] = 0;                  // huffman.c:29-31
                         }
                     }
                 }
+                __syncthreads();
+                {
+                    uint8_t *dst = out + round_pos - phase;                       // 16-byte aligned
+                    const uint64_t room = a.out_capacity > round_pos ? a.out_capacity - round_pos : 0;   // bytes of this round that fit
+                    const uint32_t nbytes = (uint32_t)min((uint64_t)round_bytes, room);
+                    const uint32_t first = phase, last = phase + nbytes;          // staging range to copy
+                    for (uint32_t u = tid; 16u * u < last; u += K2_THREADS) {
+                        const uint32_t ub = 16u * u;
+                        if (ub >= first && ub + 16u <= last) {
+                            reinterpret_cast<uint4 *>(dst)[u] = reinterpret_cast<const uint4 *>(stage)[u];
+                        } else {
+                            for (uint32_t x = max(ub, first); x < min(ub + 16u, last); ++x) dst[x] = stage[x];
+                        }
+                    }
+                }
+                round_pos += round_bytes;
+                __syncthreads();                                                  // staging area and s_warp are reused
             }
             K2_TRACE(w.t, 7);
         }

@@ -1,0 +1,368 @@
+// strip_entropy.cuh -- K1b, the strip entropy kernel: DC-difference / run-length symbols (rle.c:51-127) and their
+// Huffman codes + amplitude bits (huffman.c:121-193) for every 32-block strip, written as a strip-local bit stream.
+//
+// One warp per strip, one lane per 8x8 block, many warps per SM: the symbol walks are sparse, data-dependent and
+// latency-bound, so this kernel is kept light (no transform, few registers) and runs at two to three times the
+// occupancy of the block kernel.
+//   1. the lane's 64 quantized coefficients (int8, zig-zag order: 4 x 128-bit loads, the next strip's are requested
+//      before this strip is processed) are parked in shared memory and reduced to a 63-bit non-zero map;
+//   2. ONE table walk over the non-zero coefficients: each visit is one look-up of the ready-made symbol word
+//      (code + amplitude bits, length in the low 5 bits); the length is added to the block's bit cost and the word
+//      is cached;
+//   3. warp scan of the bit costs -> bit offset of every block inside the strip;
+//   4. the cached words are appended to the strip's bit window in shared memory (register accumulator,
+//      word-wise OR-reduction), and the window goes to the strip's slot in global memory with 128-bit stores,
+//      together with the strip record {bits, first DC, last DC}.
+// The DC predictor of a strip's first block is the last block of the previous strip (rle.c:59-70): one byte load.
+// The very first block of an image is coded by K2 (its predictor is 0, or the previous stripe's last DC in
+// multi-GPU runs).  K2 then only shifts the strips' streams to their global bit phase and stuffs.
+#pragma once
+
+#include "common.cuh"
+
+namespace jb {
+
+constexpr int STREAM_SMALL_BYTES = 1024;             // strip stream capacity of the default instantiation (32 B/block)
+constexpr int STREAM_BIG_BYTES = 5888;               // worst case: 32 blocks x 1463 bits = 5852 bytes
+constexpr int K1B_SYM_BYTES = 16384;                 // AC symbol table staged in shared memory
+
+template <bool BIGWIN>
+struct K1bCfg {
+    static constexpr int WARPS = 8;
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int CTAS_PER_SM = BIGWIN ? 1 : 3;
+    static constexpr int STREAM_BYTES = BIGWIN ? STREAM_BIG_BYTES : STREAM_SMALL_BYTES;
+    static constexpr int WIN_BYTES = STREAM_BYTES + 128;             // + slack: the bit writer may touch one word past the end
+    static constexpr int ZS_PITCH = 17;                              // words per lane of the coefficient staging area (conflict-free byte reads)
+    static constexpr int ZS_BYTES = 32 * ZS_PITCH * 4;               // 2176
+    static constexpr int CACHE_BYTES = 2048;                         // 16 cached symbol words per lane
+    static constexpr int WARP_SMEM = ZS_BYTES + CACHE_BYTES + WIN_BYTES;
+    static constexpr int SMEM = K1B_SYM_BYTES + WARPS * WARP_SMEM;
+};
+
+// ---- entropy coding helpers ------------------------------------------------------------------------------
+
+__device__ __forceinline__ int magnitude_class(int v)          // rle.c:9-22
+{
+    const int a = v < 0 ? -v : v;
+    return 32 - __clz(a);
+}
+
+// shared-memory accesses by 32-bit shared-space address: keeps the symbol loops free of the
+// generic-to-shared address arithmetic the compiler otherwise repeats at every access
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v, bool enable)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p red.shared.or.b32 [%0], %1;\n}"
+                 :: "r"(saddr), "r"(v), "r"((uint32_t)enable) : "memory");
+}
+
+// MSB-first bit appender with a 32-bit register accumulator, flushed word-wise into the zeroed
+// shared-memory window with OR-reductions (the first and last word of a block are shared with its
+// neighbours).  Branch-free: the flush is predicated.
+struct BitWriter {
+    uint32_t waddr;       // shared-space address of the window word being filled
+    uint32_t acc, fill;
+    __device__ __forceinline__ void start(uint32_t win_saddr, uint32_t relbit)
+    {
+        waddr = win_saddr + ((relbit >> 5) << 2);
+        fill = relbit & 31u;
+        acc = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t vl, uint32_t n)           // n in 1..27 bits, left-aligned in vl
+    {
+        acc |= vl >> fill;
+        fill += n;
+        const bool full = fill >= 32u;
+        red_or_shared(waddr, acc, full);
+        fill &= 31u;
+        waddr += full ? 4u : 0u;
+        acc = full ? vl << (n - fill) : acc;                               // the bits that did not fit (none if fill == 0)
+    }
+    __device__ __forceinline__ void finish() { red_or_shared(waddr, acc, fill != 0u); }
+};
+
+constexpr int SYM_CACHE = 16;        // cached symbols per block (lane-interleaved words in the dead Y tile: 16 x 32 x 4 = 2048 bytes)
+
+// Walk 1 -- the ONLY table walk: the lane visits the non-zero AC coefficients of its block (map mlo/mhi, bit k <->
+// zig-zag position k; rle.c:83-123).  Each visit is one look-up in the symbol table sym[run & 15][value & 255] =
+// (Huffman code << size | amplitude bits) left-aligned with the total length in the low 5 bits, i.e. huffman.c:164-173
+// applied to the symbol rle.c:106-113 would have produced; slot [0][0] carries EOB and [0][0x80] ZRL.  The entry's
+// length is added to the block's bit cost and the entry itself is parked in the lane's symbol cache (entry j of lane l
+// at word 32 j + l: conflict-free whatever j the lanes are at), so that the emit walk is a plain stream of cached
+// words.  A block with more symbols than the cache holds stops caching at a coefficient boundary and leaves the rest
+// (mask + previous position) to emit_tail.
+struct SymWalk {
+    uint32_t bits;        // AC bit cost incl. ZRLs and EOB
+    uint32_t cnt;         // cached entries (including the DC entry the caller placed first)
+    uint32_t rest_lo, rest_hi;   // non-zero positions NOT cached
+    int rest_prev;        // position of the last cached non-zero; -1: everything (incl. EOB) is cached
+    int last;             // position of the block's last non-zero
+};
+
+__device__ __forceinline__ SymWalk cache_symbols(uint32_t zs, uint32_t mlo, uint32_t mhi, uint32_t sym, uint32_t cache, uint32_t cnt0)
+{
+    SymWalk w;
+    w.bits = 0;
+    w.cnt = cnt0;
+    w.rest_lo = w.rest_hi = 0;
+    w.rest_prev = -1;
+    const uint32_t zrl = lds_u32(sym + 4u * 0x80u), eob = lds_u32(sym);
+    int prev = 0;
+    bool caching = true;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? mhi : mlo;
+#pragma unroll 1
+        while (m) {
+            const int k = 32 * half + __ffs((int)m) - 1;
+            const uint32_t byte = lds_u8(zs + (uint32_t)k);
+            const uint32_t run = (uint32_t)(k - prev - 1), nz = run >> 4;
+            const uint32_t e = lds_u32(sym + 4u * (((run & 15u) << 8) | byte));
+            w.bits += nz * (zrl & 31u) + (e & 31u);                                   // ZRLs: rle.c:99-103
+            if (caching) {
+                if (w.cnt + nz < (uint32_t)SYM_CACHE) {
+                    for (uint32_t z = 0; z < nz; ++z) sts_u32(cache + 128u * w.cnt++, zrl);
+                    sts_u32(cache + 128u * w.cnt++, e);
+                } else {                                                               // cache full: the rest goes the long way
+                    caching = false;
+                    w.rest_lo = half ? 0u : m;
+                    w.rest_hi = half ? m : mhi;
+                    w.rest_prev = prev;
+                }
+            }
+            m &= m - 1;
+            prev = k;
+        }
+    }
+    w.last = prev;
+    if (prev < 63) {                                                                   // EOB, rle.c:121-123
+        w.bits += eob & 31u;
+        if (caching) {
+            if (w.cnt < (uint32_t)SYM_CACHE) sts_u32(cache + 128u * w.cnt++, eob);
+            else w.rest_prev = prev;                                                   // only the EOB is left for emit_tail
+        }
+    }
+    return w;
+}
+
+// the symbols that did not fit the cache: positions in (rest_lo, rest_hi) after `prev`, then EOB
+__device__ __noinline__ BitWriter emit_tail(BitWriter bw, uint32_t zs, uint32_t rest_lo, uint32_t rest_hi, int prev, uint32_t sym)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? rest_hi : rest_lo;
+#pragma unroll 1
+        while (m) {
+            const int k = 32 * half + __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint32_t byte = lds_u8(zs + (uint32_t)k);
+            int run = k - prev - 1;
+            prev = k;
+            if (run >= 16) {                                                           // ZRL, rle.c:99-103
+                const uint32_t z = lds_u32(sym + 4u * 0x80u);
+                do {
+                    bw.put(z & ~31u, z & 31u);
+                    run -= 16;
+                } while (run >= 16);
+            }
+            const uint32_t e = lds_u32(sym + 4u * (((uint32_t)run << 8) | byte));
+            bw.put(e & ~31u, e & 31u);
+        }
+    }
+    if (prev < 63) {                                                                   // EOB, rle.c:121-123
+        const uint32_t e = lds_u32(sym);
+        bw.put(e & ~31u, e & 31u);
+    }
+    return bw;
+}
+
+
+// geometry + buffers of the strip entropy kernel
+struct StripArgs {
+    const int8_t *coef;            // [blocks][64] zig-zag int8 (K1)
+    const uint8_t *tables;         // device table block
+    StripRec *strips;              // [total_strips]
+    uint32_t *strip_bits;          // [total_strips] compact copy of StripRec.bits
+    uint8_t *streams;              // [total_strips][slot_bytes]: the strip's bits, MSB first in 32-bit words
+    uint32_t slot_bytes;           // multiple of 16, <= the instantiation's STREAM_BYTES
+    uint32_t *dbg_blkinfo;         // optional stage tap: bit offset inside the strip | last non-zero << 16
+    uint32_t *err;
+    uint32_t total_strips;
+    uint32_t spr, bw, bh;          // strips per block row, blocks per block row, block rows per image
+    uint64_t blocks_per_image;
+};
+
+template <bool BIGWIN>
+__global__ void __launch_bounds__(K1bCfg<BIGWIN>::THREADS, K1bCfg<BIGWIN>::CTAS_PER_SM)
+k_strip_entropy(const StripArgs a)
+{
+    using Cfg = K1bCfg<BIGWIN>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wbase = smem + K1B_SYM_BYTES + warp * Cfg::WARP_SMEM;
+    uint32_t *zs = reinterpret_cast<uint32_t *>(wbase) + lane * Cfg::ZS_PITCH;          // this lane's 64 coefficient bytes
+    uint32_t *win = reinterpret_cast<uint32_t *>(wbase + Cfg::ZS_BYTES + Cfg::CACHE_BYTES);   // the strip's bit window
+    uint32_t smem_sa = smem_u32(smem);
+    asm volatile("mov.b32 %0, %0;" : "+r"(smem_sa));             // opaque: computed once, not rematerialised at every use
+    const uint32_t sym_sa = smem_sa;                             // symbol table at offset 0
+    const uint32_t zs_sa = smem_sa + (uint32_t)(reinterpret_cast<uint8_t *>(zs) - smem);
+    const uint32_t cache_sa = smem_sa + (uint32_t)(wbase + Cfg::ZS_BYTES - smem) + 4u * (uint32_t)lane;
+    const uint32_t win_sa = smem_sa + (uint32_t)(reinterpret_cast<uint8_t *>(win) - smem);
+    __shared__ uint32_t s_dc[16];                                // DC codes: (code << 8) | len per size class
+    __shared__ __align__(8) uint64_t s_bar;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, K1B_SYM_BYTES);                   // 16 KB, one TMA bulk copy; awaited before the first walk
+        bulk_g2s(smem, a.tables + TBL_SYM, K1B_SYM_BYTES, &s_bar);
+    }
+    if (threadIdx.x < 16) s_dc[threadIdx.x] = reinterpret_cast<const uint32_t *>(a.tables + TBL_DC_CODE)[threadIdx.x];
+    __syncthreads();
+
+    const uint32_t stride = gridDim.x * Cfg::WARPS;
+    const uint32_t per_image = a.bh * a.spr;
+    const uint32_t cap_bits = a.slot_bytes * 8u;
+    bool table_ready = false;
+
+    // strip -> (first block, blocks, first-of-image)
+    auto locate = [&](uint32_t s, uint64_t &block0, uint32_t &vb, bool &first) {
+        const uint32_t img = s / per_image, rem = s - img * per_image;
+        const uint32_t brow = rem / a.spr, sx = rem - brow * a.spr;
+        block0 = (uint64_t)img * a.blocks_per_image + (uint64_t)brow * a.bw + sx * 32u;
+        vb = min(32u, a.bw - sx * 32u);
+        first = rem == 0;
+    };
+
+    uint32_t s = blockIdx.x * Cfg::WARPS + warp;
+    uint64_t block0 = 0;
+    uint32_t vb = 0;
+    bool first = false;
+    uint4 q[4];
+    int pred = 0;                                                // lane 0: quantized DC of the block before the strip
+    if (s < a.total_strips) {
+        locate(s, block0, vb, first);
+        if ((uint32_t)lane < vb) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = src[i];
+        }
+        if (lane == 0 && !first) pred = (int)a.coef[(block0 - 1) * 64];
+    }
+    for (; s < a.total_strips; s += stride) {
+        const uint64_t my_block0 = block0;
+        const uint32_t my_vb = vb;
+        const bool my_first = first;
+        uint32_t mlo = 0, mhi = 0;                               // non-zero map of the block's AC coefficients
+        int my_dc = 0;
+        const int prev_strip_dc = pred;
+        if ((uint32_t)lane < my_vb) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                zs[4 * i] = q[i].x; zs[4 * i + 1] = q[i].y; zs[4 * i + 2] = q[i].z; zs[4 * i + 3] = q[i].w;
+                const uint32_t m16 = nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) |
+                                     (nonzero_nibble(q[i].w) << 12);
+                if (i < 2) mlo |= m16 << (16 * i);
+                else mhi |= m16 << (16 * (i - 2));
+            }
+            mlo &= ~1u;                                          // position 0 is the DC
+            my_dc = (int)(int8_t)(q[0].x & 0xFFu);
+        }
+        // request the next strip's coefficients now: their latency hides behind the walks below
+        if (s + stride < a.total_strips) {
+            locate(s + stride, block0, vb, first);
+            if ((uint32_t)lane < vb) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 64);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = src[i];
+            }
+            if (lane == 0 && !first) pred = (int)a.coef[(block0 - 1) * 64];
+        }
+        if (!table_ready) {
+            mbar_wait(&s_bar, 0);
+            table_ready = true;
+        }
+        // DC differences (rle.c:68-76): the previous lane's block, or the block before the strip for lane 0
+        bool with_dc;
+        uint32_t dc_word = 0;                                    // the DC symbol: code + amplitude bits left-aligned | length
+        {
+            int prev_dc = __shfl_up_sync(0xffffffffu, my_dc, 1);
+            if (lane == 0) prev_dc = prev_strip_dc;
+            const int diff = my_dc - prev_dc;
+            with_dc = (uint32_t)lane < my_vb && (lane > 0 || !my_first);
+            if (with_dc) {
+                const int sz = magnitude_class(diff);
+                const uint32_t dc_entry = s_dc[sz];
+                const uint32_t amp = (uint32_t)(diff > 0 ? diff : diff - 1) & ((1u << sz) - 1u);   // rle.c:24-35, huffman.c:39
+                const uint32_t n = (dc_entry & 0xFFu) + (uint32_t)sz;                               // <= 9 + 11
+                dc_word = ((((dc_entry >> 8) << sz) | amp) << (32u - n)) | n;
+            }
+        }
+        __syncwarp();
+        SymWalk sw;
+        sw.bits = sw.cnt = sw.rest_lo = sw.rest_hi = 0;
+        sw.rest_prev = -1;
+        sw.last = 0;
+        uint32_t my_bits = 0;
+        if ((uint32_t)lane < my_vb) {
+            if (with_dc) sts_u32(cache_sa, dc_word);
+            sw = cache_symbols(zs_sa, mlo, mhi, sym_sa, cache_sa, with_dc ? 1u : 0u);
+            my_bits = sw.bits + (dc_word & 31u);
+        }
+        uint32_t incl = my_bits;
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, ofs);
+            if (lane >= ofs) incl += n;
+        }
+        const uint32_t strip_total = __shfl_sync(0xffffffffu, incl, 31);
+        const bool fits = strip_total <= cap_bits;
+        const uint32_t nquads = fits ? (strip_total + 127u) >> 7 : 0u;               // 16-byte units written to the slot
+        // ---- emit the strip's bits into the zeroed window, then window -> the strip's slot ------------------------
+        for (uint32_t i = lane; i < nquads + 1; i += 32) reinterpret_cast<uint4 *>(win)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        if (fits && (uint32_t)lane < my_vb) {
+            BitWriter bw;
+            bw.start(win_sa, incl - my_bits);
+#pragma unroll 1
+            for (uint32_t j = 0; j < sw.cnt; ++j) {
+                const uint32_t e = lds_u32(cache_sa + 128u * j);
+                bw.put(e & ~31u, e & 31u);
+            }
+            if (sw.rest_prev >= 0) bw = emit_tail(bw, zs_sa, sw.rest_lo, sw.rest_hi, sw.rest_prev, sym_sa);
+            bw.finish();
+        }
+        __syncwarp();
+        {
+            uint4 *dst = reinterpret_cast<uint4 *>(a.streams + (uint64_t)s * a.slot_bytes);
+            for (uint32_t i = lane; i < nquads; i += 32) dst[i] = reinterpret_cast<const uint4 *>(win)[i];
+            const int first_dc = __shfl_sync(0xffffffffu, my_dc, 0);
+            if ((uint32_t)lane == my_vb - 1) {
+                a.strips[s] = StripRec{strip_total, (int16_t)first_dc, (int16_t)my_dc};
+                a.strip_bits[s] = strip_total;
+                if (!fits) atomicOr(a.err, ERRBIT_WORKSPACE);
+            }
+            if (a.dbg_blkinfo && (uint32_t)lane < my_vb)          // stage tap for the parity tests
+                a.dbg_blkinfo[my_block0 + (uint32_t)lane] = (incl - my_bits) | ((uint32_t)sw.last << 16);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace jb

@@ -153,7 +153,7 @@ class DeviceEncoder:
         calls = (C.c_uint64 * 8)()
         check(self.lib.jpegb200_encoder_kernel_times(self.handle, ms, calls, int(reset)), "kernel_times")
         return {"ms": list(ms), "calls": [int(c) for c in calls],
-                "names": ["fused_block", "scan_pack_stuff", "batch_layout", "batch_compact", "frame_files", "", "", ""]}
+                "names": ["fused_block", "merge_stuff", "batch_layout", "batch_compact", "frame_files", "strip_entropy", "", ""]}
 
     def coefficients(self, nblocks: int) -> np.ndarray:
         out = np.empty((nblocks, 64), np.int16)
