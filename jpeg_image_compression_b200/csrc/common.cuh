@@ -189,6 +189,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // the mbarrier receives one arrival once all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {

@@ -13,8 +13,8 @@
 //   3. transform + quantization, one of
 //      TC = true  (default): the 64-term sums of all 64 coefficients run on the tensor cores.  A tile of 128
 //                 blocks (4 strips = 4 warps) is one tcgen05.mma chain D[128 x 128] = A[128 x 64] * B^T: A = the
-//                 level-shifted luma values as fp16 integers, written by each lane for its block straight into
-//                 tensor memory (tcgen05.st); B = the reference's own LUT products cos[r][u]*cos[c][v] in 22-bit
+//                 level-shifted luma values as fp16 integers, written by the luma pass straight into the UMMA
+//                 operand layout in shared memory; B = the reference's own LUT products cos[r][u]*cos[c][v] in 22-bit
 //                 fixed point, split into two 11-bit integer limbs held as fp16 (shared memory, UMMA K-major
 //                 layout).  Every product and partial sum is an integer below 2^24, so the fp32 accumulators in
 //                 TMEM hold the EXACT integer sums; tcgen05.ld hands each lane its block's 128 limb sums, 16
@@ -38,6 +38,8 @@
 
 #include <cuda.h>          // CUtensorMap (type only; the encoder function is looked up at run time)
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace jb {
@@ -50,20 +52,22 @@ constexpr int TMAP_ROW_BYTES = 768;                  // a tensor-map box is dens
 constexpr int K1_BMAT_BYTES = 16384;                 // limb matrix of the tensor-core transform
 
 // Launch shape and shared-memory carve-up of the two instantiations.
-//   TC: one CTA per SM, warps in groups of four (a 128-block MMA tile); TMEM: 160 columns per group, 3 groups fit
+//   TC: one CTA of 16 warps per SM, warps in groups of four (a 128-block MMA tile: 16 KB of A in shared memory and
+//       128 accumulator columns of tensor memory per group -- 4 x 128 = all 512 columns)
 template <bool TC>
 struct K1Cfg {
-    static constexpr int WARPS = TC ? 12 : 8;
+    static constexpr int WARPS = TC ? 16 : 8;
     static constexpr int THREADS = WARPS * 32;
     static constexpr int CTAS_PER_SM = TC ? 1 : 2;
     static constexpr int GROUPS = WARPS / 4;
     static constexpr int WARP_SMEM = RAW_BYTES + Y_BYTES;             // 8320 = 65 x 128
-    static constexpr int TABLE_BYTES = TC ? K1_BMAT_BYTES : 0;
+    static constexpr int A_TILE_BYTES = 16384;                       // fp16 [128 blocks][64] in UMMA K-major layout
+    static constexpr int TABLE_BYTES = TC ? K1_BMAT_BYTES + GROUPS * A_TILE_BYTES : 0;
     static constexpr int SMEM = TABLE_BYTES + WARPS * WARP_SMEM;
-    static constexpr int TMEM_COLS = 512;                            // 160 per group, power of two
+    static constexpr int TMEM_COLS = 512;
     static_assert(WARP_SMEM % 128 == 0, "per-warp region must keep the tensor-map tiles 128-byte aligned");
 };
-constexpr int TC_GROUP_COLS = 160;                   // 128 accumulator columns (2 limbs x 64) + 32 columns of A
+constexpr int TC_GROUP_COLS = 128;                   // accumulator columns per group: 2 limbs x 64 coefficients
 constexpr uint32_t TC_IDESC = (1u << 4)              // D: fp32
                               | (0u << 7) | (0u << 10)      // A, B: fp16
                               | (0u << 15) | (0u << 16)     // both K-major
@@ -167,6 +171,17 @@ __device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2,
     const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), wt_lo, 0u);
     const uint32_t y3 = __dp4a(w2, wt_hi, 0u);
     return __byte_perm(__byte_perm(y0, y1, 0x0051u), __byte_perm(y2, y3, 0x0051u), 0x5410u);
+}
+
+// four luma bytes -> four level-shifted fp16 values (converter.c:84): 0x64yy is the fp16 1024 + yy, and subtracting
+// 1152 is exact
+__device__ __forceinline__ uint2 y4_to_half4(uint32_t y)
+{
+    const uint32_t lo = __byte_perm(y, 0x64646464u, 0x4140u), hi = __byte_perm(y, 0x64646464u, 0x4342u);
+    uint2 r;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r.x) : "r"(lo), "r"(0xE480E480u));
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r.y) : "r"(hi), "r"(0xE480E480u));
+    return r;
 }
 
 __device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
@@ -315,7 +330,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     const CUtensorMap *tmap = g.use_tmap ? &tmap_param : nullptr;
     const uint32_t raw_pitch = g.use_tmap ? TMAP_ROW_BYTES : RAW_PITCH;
     uint8_t *ybuf = raw + RAW_BYTES;
-    __shared__ __align__(8) uint64_t s_bar[WARPS + 1 + 3];       // per-warp tile barriers, the table barrier, per-group MMA barriers
+    __shared__ __align__(8) uint64_t s_bar[WARPS + 1 + 4];       // per-warp tile barriers, the table barrier, per-group MMA barriers
     __shared__ uint32_t s_tmem;
 
     K1_TRACE(0);
@@ -359,11 +374,14 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
         lookback_state[i] = 0;
     K1_TRACE(1);
 
-    // tensor memory of this warp's group: accumulators at column 160 * group, A at + 128; the warp owns lanes 32 * (warp % 4)
+    // tensor memory of this warp's group: accumulators at column 128 * group; the warp owns lanes 32 * (warp % 4).
+    // A operand of the group: 16 KB after the limb matrix, this warp's 32 blocks = 4 KB of it.  Layout (UMMA K-major,
+    // no swizzle): block b, pixel row y, column x -> (b/8)*1024 + y*128 + (b%8)*16 + 2x, i.e. a core matrix (8 blocks x
+    // 8 pixels of one row) is 128 contiguous bytes, LBO (next pixel row) = 128, SBO (next 8 blocks) = 1024.
     const int group = warp >> 2, quad = warp & 3;
     const uint32_t tmem_d = TC ? s_tmem + (uint32_t)(group * TC_GROUP_COLS) : 0u;
-    const uint32_t tmem_a = tmem_d + 128u;
     const uint32_t tmem_lane = (uint32_t)(quad * 32) << 16;
+    uint8_t *a_warp = smem + K1_BMAT_BYTES + group * Cfg::A_TILE_BYTES + quad * 4096;
     uint64_t *mma_bar = &s_bar[WARPS + 1 + group];
     uint32_t mma_phase = 0;
 
@@ -391,8 +409,14 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                 for (int r = 0; r < 8; ++r) {
                     const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
                     uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
-                    yo[lane] = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi);
-                    yo[lane + 32] = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
+                    const uint32_t ya = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi), yb = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
+                    yo[lane] = ya;
+                    yo[lane + 32] = yb;
+                    if (TC) {
+                        uint8_t *ap = a_warp + ((lane >> 4) << 10) + (r << 7) + (((lane >> 1) & 7) << 4) + ((lane & 1) << 3);
+                        *reinterpret_cast<uint2 *>(ap) = y4_to_half4(ya);
+                        *reinterpret_cast<uint2 *>(ap + 2048) = y4_to_half4(yb);
+                    }
                 }
             } else {
                 // any width / any base alignment: funnel-shift the row to word alignment
@@ -405,8 +429,10 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                         const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch) + (mis >> 2) + 3 * gc;
                         const uint32_t sh = (mis & 3u) * 8u;
                         const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
-                        reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] =
-                            luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh), g.wt_lo, g.wt_hi);
+                        const uint32_t yv = luma4(__funnelshift_r(q0, q1, sh), __funnelshift_r(q1, q2, sh), __funnelshift_r(q2, q3, sh), g.wt_lo, g.wt_hi);
+                        reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH)[gc] = yv;
+                        if (TC)
+                            *reinterpret_cast<uint2 *>(a_warp + ((gc >> 4) << 10) + (r << 7) + (((gc >> 1) & 7) << 4) + ((gc & 1) << 3)) = y4_to_half4(yv);
                     }
                 }
             }
@@ -424,7 +450,14 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
             if (padpx > 0) {
                 if (lane < padpx) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) ybuf[r * Y_PITCH + me.npx + lane] = ybuf[r * Y_PITCH + me.npx - 1];
+                    for (int r = 0; r < 8; ++r) {
+                        const uint8_t yv = ybuf[r * Y_PITCH + me.npx - 1];
+                        ybuf[r * Y_PITCH + me.npx + lane] = yv;
+                        if (TC) {
+                            const int px = me.npx + lane, b = px >> 3;
+                            *reinterpret_cast<__half *>(a_warp + ((b >> 3) << 10) + (r << 7) + ((b & 7) << 4) + ((px & 7) << 1)) = __int2half_rn((int)yv - 128);
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -433,8 +466,20 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
 
         uint32_t zw[16], xw[16];                                 // quantized coefficients (zig-zag, int8) / bracket disagreement
         if (TC) {
-            // ---- A operand: the block's 64 level-shifted luma values as fp16, K order = raster, into tensor memory --
+            if (valid) fence_proxy_async();                      // the luma pass wrote this warp's quarter of A (generic proxy -> MMA)
+            tc_fence_before_sync();
+            named_bar_sync(1 + group, 128);                      // the tile's four A quarters are in shared memory
+            if (quad == 0 && lane == 0) {
+                mbar_wait(table_bar, 0);                       // the limb matrix (immediate after the first tile)
+                tc_fence_after_sync();
+                const uint32_t b_sa = smem_u32(smem), a_sa = b_sa + K1_BMAT_BYTES + (uint32_t)(group * Cfg::A_TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)                   // K = 64 in four steps of 16 (two pixel rows); B: 4 KB per step, LBO 128, SBO 256
+                    umma_f16_ss(tmem_d, umma_desc(a_sa + 256u * ks, 128u, 1024u), umma_desc(b_sa + 4096u * ks, 128u, 256u), TC_IDESC, ks > 0 ? 1u : 0u);
+                umma_commit(mma_bar);
+            }
             if (valid) {
+                // block statistics from the Y bytes while the MMA runs: A = sum |Y - 128|, sum Y, Ac = sum |Y - mean|
                 uint32_t sumy = 0;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -446,35 +491,13 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                     sumy = __vsadu4(v.x, 0u) + sumy;
                     sumy = __vsadu4(v.y, 0u) + sumy;
                 }
-                uint32_t ar[32];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    // 0x64yy is the fp16 1024 + yy; subtracting 1152 is exact: yy - 128 (converter.c:84)
-                    const uint32_t lo = __byte_perm(yw[j], 0x64646464u, 0x4140u), hi = __byte_perm(yw[j], 0x64646464u, 0x4342u);
-                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(ar[2 * j]) : "r"(lo), "r"(0xE480E480u));
-                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(ar[2 * j + 1]) : "r"(hi), "r"(0xE480E480u));
-                }
-                JB_TMEM_ST32(tmem_a + tmem_lane, ar);
-                tmem_wait_st();
                 x00 = (float)((int)sumy - 8192);
-                // Ac = sum |Y - m|, m = the block's rounded mean luma
-                const int mean = (int)rintf(x00 * 0.015625f) + 128;
-                const uint32_t m4 = (uint32_t)mean * 0x01010101u;
+                {
+                    const int mean = (int)rintf(x00 * 0.015625f) + 128;
+                    const uint32_t m4 = (uint32_t)mean * 0x01010101u;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) absmean = __vsadu4(yw[j], m4) + absmean;
-            }
-            tc_fence_before_sync();
-            named_bar_sync(1 + group, 128);                      // the tile's four A quarters are in tensor memory
-            if (quad == 0 && lane == 0) {
-                mbar_wait(table_bar, 0);                       // the limb matrix (immediate after the first tile)
-                tc_fence_after_sync();
-                const uint32_t b_sa = smem_u32(smem);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)                   // K = 64 in four steps of 16; B: 4 KB per step, LBO 128, SBO 256
-                    umma_f16_ts(tmem_d, tmem_a + 8u * ks, umma_desc(b_sa + 4096u * ks, 128u, 256u), TC_IDESC, ks > 0 ? 1u : 0u);
-                umma_commit(mma_bar);
-            }
-            if (valid) {
+                    for (int j = 0; j < 16; ++j) absmean = __vsadu4(yw[j], m4) + absmean;
+                }
                 mbar_wait(mma_bar, mma_phase);
                 tc_fence_after_sync();
                 // guard half-width in fixed-point units

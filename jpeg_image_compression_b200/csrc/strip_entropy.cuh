@@ -72,32 +72,28 @@ __device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v, bool e
                  :: "r"(saddr), "r"(v), "r"((uint32_t)enable) : "memory");
 }
 
-// MSB-first bit appender with a 32-bit register accumulator, flushed word-wise into the zeroed
-// shared-memory window with OR-reductions (the first and last word of a block are shared with its
-// neighbours).  Branch-free: the flush is predicated.
+// MSB-first bit appender: every symbol is OR-reduced into the zeroed shared-memory window at its absolute bit
+// position (two word-wise reductions; the second one is a no-op when the symbol does not cross a word boundary).
+// No register accumulator, hence no loop-carried dependency besides the position and no conditional flush.
 struct BitWriter {
-    uint32_t waddr;       // shared-space address of the window word being filled
-    uint32_t acc, fill;
+    uint32_t win;         // shared-space address of the window
+    uint32_t pos;         // bit position of the next symbol
     __device__ __forceinline__ void start(uint32_t win_saddr, uint32_t relbit)
     {
-        waddr = win_saddr + ((relbit >> 5) << 2);
-        fill = relbit & 31u;
-        acc = 0;
+        win = win_saddr;
+        pos = relbit;
     }
-    __device__ __forceinline__ void put(uint32_t vl, uint32_t n)           // n in 1..27 bits, left-aligned in vl
+    __device__ __forceinline__ void put(uint32_t vl, uint32_t n)           // n in 1..27 bits, left-aligned in vl (low bits zero)
     {
-        acc |= vl >> fill;
-        fill += n;
-        const bool full = fill >= 32u;
-        red_or_shared(waddr, acc, full);
-        fill &= 31u;
-        waddr += full ? 4u : 0u;
-        acc = full ? vl << (n - fill) : acc;                               // the bits that did not fit (none if fill == 0)
+        const uint32_t sh = pos & 31u, waddr = win + ((pos >> 5) << 2);
+        const uint32_t hi = vl >> sh, lo = __funnelshift_r(0u, vl, sh);       // (vl : 0) >> sh, low word = the bits that spill over
+        asm volatile("red.shared.or.b32 [%0], %1;\n\tred.shared.or.b32 [%0+4], %2;" :: "r"(waddr), "r"(hi), "r"(lo) : "memory");
+        pos += n;
     }
-    __device__ __forceinline__ void finish() { red_or_shared(waddr, acc, fill != 0u); }
+    __device__ __forceinline__ void finish() {}
 };
 
-constexpr int SYM_CACHE = 16;        // cached symbols per block (lane-interleaved words in the dead Y tile: 16 x 32 x 4 = 2048 bytes)
+constexpr int SYM_CACHE = 16;        // cached symbols per block (lane-interleaved words: 16 x 32 x 4 = 2048 bytes per warp)
 
 // Walk 1 -- the ONLY table walk: the lane visits the non-zero AC coefficients of its block (map mlo/mhi, bit k <->
 // zig-zag position k; rle.c:83-123).  Each visit is one look-up in the symbol table sym[run & 15][value & 255] =
@@ -105,26 +101,24 @@ constexpr int SYM_CACHE = 16;        // cached symbols per block (lane-interleav
 // applied to the symbol rle.c:106-113 would have produced; slot [0][0] carries EOB and [0][0x80] ZRL.  The entry's
 // length is added to the block's bit cost and the entry itself is parked in the lane's symbol cache (entry j of lane l
 // at word 32 j + l: conflict-free whatever j the lanes are at), so that the emit walk is a plain stream of cached
-// words.  A block with more symbols than the cache holds stops caching at a coefficient boundary and leaves the rest
-// (mask + previous position) to emit_tail.
+// words.  Caching stops at the first coefficient that needs a ZRL (zero run >= 16, rle.c:99-103) or does not fit the
+// cache any more; that coefficient and everything after it (mask + previous position) is left to emit_tail.
 struct SymWalk {
     uint32_t bits;        // AC bit cost incl. ZRLs and EOB
-    uint32_t cnt;         // cached entries (including the DC entry the caller placed first)
+    uint32_t cend;        // shared-space address one past the last cached entry
     uint32_t rest_lo, rest_hi;   // non-zero positions NOT cached
     int rest_prev;        // position of the last cached non-zero; -1: everything (incl. EOB) is cached
     int last;             // position of the block's last non-zero
 };
 
-__device__ __forceinline__ SymWalk cache_symbols(uint32_t zs, uint32_t mlo, uint32_t mhi, uint32_t sym, uint32_t cache, uint32_t cnt0)
+__device__ __forceinline__ SymWalk cache_symbols(uint32_t zs, uint32_t mlo, uint32_t mhi, uint32_t sym, uint32_t cptr, uint32_t climit)
 {
     SymWalk w;
     w.bits = 0;
-    w.cnt = cnt0;
     w.rest_lo = w.rest_hi = 0;
     w.rest_prev = -1;
-    const uint32_t zrl = lds_u32(sym + 4u * 0x80u), eob = lds_u32(sym);
+    const uint32_t zrl_len = lds_u32(sym + 4u * 0x80u) & 31u, eob = lds_u32(sym);
     int prev = 0;
-    bool caching = true;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t m = half ? mhi : mlo;
@@ -132,15 +126,14 @@ __device__ __forceinline__ SymWalk cache_symbols(uint32_t zs, uint32_t mlo, uint
         while (m) {
             const int k = 32 * half + __ffs((int)m) - 1;
             const uint32_t byte = lds_u8(zs + (uint32_t)k);
-            const uint32_t run = (uint32_t)(k - prev - 1), nz = run >> 4;
-            const uint32_t e = lds_u32(sym + 4u * (((run & 15u) << 8) | byte));
-            w.bits += nz * (zrl & 31u) + (e & 31u);                                   // ZRLs: rle.c:99-103
-            if (caching) {
-                if (w.cnt + nz < (uint32_t)SYM_CACHE) {
-                    for (uint32_t z = 0; z < nz; ++z) sts_u32(cache + 128u * w.cnt++, zrl);
-                    sts_u32(cache + 128u * w.cnt++, e);
-                } else {                                                               // cache full: the rest goes the long way
-                    caching = false;
+            const uint32_t run = (uint32_t)(k - prev - 1);
+            const uint32_t e = lds_u32(sym + ((((run & 15u) << 8) | byte) << 2));
+            w.bits += (run >> 4) * zrl_len + (e & 31u);                                // ZRLs: rle.c:99-103
+            if (w.rest_prev < 0) {                                                     // still caching
+                if (run < 16u && cptr < climit) {
+                    sts_u32(cptr, e);
+                    cptr += 128u;
+                } else {                                                               // the rest goes the long way
                     w.rest_lo = half ? 0u : m;
                     w.rest_hi = half ? m : mhi;
                     w.rest_prev = prev;
@@ -153,11 +146,16 @@ __device__ __forceinline__ SymWalk cache_symbols(uint32_t zs, uint32_t mlo, uint
     w.last = prev;
     if (prev < 63) {                                                                   // EOB, rle.c:121-123
         w.bits += eob & 31u;
-        if (caching) {
-            if (w.cnt < (uint32_t)SYM_CACHE) sts_u32(cache + 128u * w.cnt++, eob);
-            else w.rest_prev = prev;                                                   // only the EOB is left for emit_tail
+        if (w.rest_prev < 0) {
+            if (cptr < climit) {
+                sts_u32(cptr, eob);
+                cptr += 128u;
+            } else {
+                w.rest_prev = prev;                                                    // only the EOB is left for emit_tail
+            }
         }
     }
+    w.cend = cptr;
     return w;
 }
 
@@ -316,13 +314,14 @@ k_strip_entropy(const StripArgs a)
         }
         __syncwarp();
         SymWalk sw;
-        sw.bits = sw.cnt = sw.rest_lo = sw.rest_hi = 0;
+        sw.bits = sw.rest_lo = sw.rest_hi = 0;
+        sw.cend = cache_sa;
         sw.rest_prev = -1;
         sw.last = 0;
         uint32_t my_bits = 0;
         if ((uint32_t)lane < my_vb) {
             if (with_dc) sts_u32(cache_sa, dc_word);
-            sw = cache_symbols(zs_sa, mlo, mhi, sym_sa, cache_sa, with_dc ? 1u : 0u);
+            sw = cache_symbols(zs_sa, mlo, mhi, sym_sa, cache_sa + (with_dc ? 128u : 0u), cache_sa + 128u * SYM_CACHE);
             my_bits = sw.bits + (dc_word & 31u);
         }
         uint32_t incl = my_bits;
@@ -341,8 +340,8 @@ k_strip_entropy(const StripArgs a)
             BitWriter bw;
             bw.start(win_sa, incl - my_bits);
 #pragma unroll 1
-            for (uint32_t j = 0; j < sw.cnt; ++j) {
-                const uint32_t e = lds_u32(cache_sa + 128u * j);
+            for (uint32_t cp = cache_sa; cp != sw.cend; cp += 128u) {
+                const uint32_t e = lds_u32(cp);
                 bw.put(e & ~31u, e & 31u);
             }
             if (sw.rest_prev >= 0) bw = emit_tail(bw, zs_sa, sw.rest_lo, sw.rest_hi, sw.rest_prev, sym_sa);

@@ -14,16 +14,17 @@ d = enc.synth(w, h, 1, 1, 20)
 for _ in range(5):
     enc.encode_device(d, w, h, 1)
 torch.cuda.synchronize()
-ntiles = (((w + 255) // 256) * ((h + 7) // 8) + 7) // 8
+ntiles = (((w + 255) // 256) * ((h + 7) // 8) + 15) // 16      # K2_TILE_STRIPS = 16
 tr = np.zeros((ntiles, 8), np.uint64)
 check(enc.lib.jpegb200_encoder_read_trace(enc.handle, tr.ctypes.data, ntiles), "trace")
 t = tr.astype(np.int64)
 t0 = t[:, 0].min()
-names = ["start", "loaded", "bitprefix", "zeroed", "packed", "ffcount", "fflook", "written"]
+names = ["start", "prefix", "offsets", "(unused)", "assembled", "ffcount", "fflook", "written"]
 print("tiles", ntiles, "kernel span us", (t[:, 7].max() - t0) / 1e3)
 for i, n in enumerate(names):
     rel = (t[:, i] - t0) / 1e3
     print(f"{n:10s} min {rel.min():6.2f} median {np.median(rel):6.2f} max {rel.max():6.2f}")
+t[:, 3] = t[:, 2]
 for i in range(1, 8):
     d_ = (t[:, i] - t[:, i - 1]) / 1e3
     print(f"phase {names[i-1]:>9s}->{names[i]:<9s}: median {np.median(d_):5.2f} p90 {np.percentile(d_, 90):5.2f} max {d_.max():5.2f}")
