@@ -98,6 +98,31 @@ __device__ __forceinline__ uint32_t masked_word(const uint32_t *win, uint32_t i,
     return v;
 }
 
+// the four window words i..i+3 restricted to the owned window bytes [wb0, wb1), and the number of 0xFF bytes among them
+__device__ __forceinline__ uint32_t masked_quad(const uint32_t *win, uint32_t i, uint32_t wb0, uint32_t wb1, uint32_t v[4])
+{
+    const uint4 q = *reinterpret_cast<const uint4 *>(win + i);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    if (4u * i < wb0 || 4u * i + 16u > wb1) {                  // only a tile's first and last group are ragged
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = 4u * (i + j), hi = lo + 4u;
+            if (lo < wb0) v[j] &= wb0 - lo >= 4u ? 0u : 0xFFFFFFFFu >> (8u * (wb0 - lo));
+            if (hi > wb1) v[j] &= wb1 > lo ? 0xFFFFFFFFu << (8u * (hi - wb1)) : 0u;
+        }
+    }
+    return count_ff_bytes(v[0]) + count_ff_bytes(v[1]) + count_ff_bytes(v[2]) + count_ff_bytes(v[3]);
+}
+
+// OR `n` left-aligned bits into the zeroed window at bit position `pos` (one thread; used for the few odd segments)
+__device__ __forceinline__ void window_put(uint32_t *win, uint32_t pos, uint32_t vl)
+{
+    const uint32_t sh = pos & 31u;
+    const uint32_t hi = vl >> sh, lo = __funnelshift_r(0u, vl, sh);
+    if (hi) atomicOr(win + (pos >> 5), hi);
+    if (lo) atomicOr(win + (pos >> 5) + 1, lo);
+}
+
 // 32 bits of a segment's stream starting at bit `off` of the segment (off may be negative: the segment starts inside
 // the word), restricted to the segment's `len` bits.  src: the segment's words (bit 31 of word 0 is its first bit).
 __device__ __forceinline__ uint32_t segment_bits(const uint32_t *src, int off, uint32_t len)
@@ -131,6 +156,7 @@ struct PendingTile {
     uint64_t w0;         // stream word index of window word 0
     uint64_t B0, B1;     // owned stream bytes [B0, B1)
     uint32_t tile_ff;    // 0xFF bytes among them
+    uint32_t nwords;     // window words in use (zeroed again after the write-out)
 };
 
 // The windows are sized at launch (dynamic shared memory): K2_TILE_STRIPS x the strip slot size.  An image that needs
@@ -149,6 +175,7 @@ k_merge_stuff(const PackArgs a, const int win_words)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_next_tile = atomicAdd(a.tile_counter, 1ull);
+    for (int i = tid; i < win_words / 2; i += K2_THREADS) reinterpret_cast<uint4 *>(k2_smem_words)[i] = make_uint4(0u, 0u, 0u, 0u);   // both windows
     const int32_t dc_pred0 = a.dyn ? a.dyn->dc_pred0 : (int32_t)a.dc_pred0;
     const uint32_t bit_phase = a.dyn ? a.dyn->bit_phase : a.bit_phase;
     const uint64_t origin = ((uint64_t)bit_phase + 7) >> 3;       // first stream byte this image/stripe owns
@@ -250,39 +277,41 @@ k_merge_stuff(const PackArgs a, const int win_words)
             }
             K2_TRACE(t, 2);
 
-            // ---- 2. assemble the tile's words: shift every overlapping segment to the global bit phase ---------------
-            {
-                const int rel0 = -(int)(uint32_t)(begin - (w0 << 5));          // tile-relative bit position of window word 0
+            // ---- 2. assemble the tile's part of the stream: every strip is shifted to the global bit phase -------------
+            // A warp takes every fourth strip; a lane loads stream word i (coalesced), gets word i-1 from its neighbour
+            // and OR-reduces ((word i-1 : word i) >> phase) into the zeroed window.  The strips' streams are zero beyond
+            // their last bit (K1b), so nothing has to be masked.
+            if (fits) {
+                const uint32_t rel_begin = (uint32_t)(begin - (w0 << 5));         // bit position of the tile's first bit in the window
                 const uint8_t *tile_streams = a.streams + (strip_base + strip0) * (uint64_t)a.slot_bytes;
-                for (uint32_t j = tid; j < nwords; j += K2_THREADS) {
-                    const int P = rel0 + 32 * (int)j;                          // this word covers tile bits [P, P + 32)
-                    const uint32_t Pc = P > 0 ? (uint32_t)P : 0u;
-                    uint32_t acc = 0;
-                    // first segment that ends after Pc: branch-free binary search in the padded table
-                    uint32_t k = 0;
-#pragma unroll
-                    for (uint32_t step = 16; step > 0; step >>= 1)
-                        if (s_seg_end[k + step - 1] <= Pc) k += step;
-                    uint32_t seg_begin = k > 0 ? s_seg_end[k - 1] : 0u;
-                    while (k <= nstrips && (int)seg_begin < P + 32) {
-                        const uint32_t seg_end = s_seg_end[k], len = seg_end - seg_begin;
-                        if (len) {
-                            const uint32_t *src = k == 0 ? s_pseudo : reinterpret_cast<const uint32_t *>(tile_streams + (k - 1) * (uint64_t)a.slot_bytes);
-                            acc |= segment_bits(src, P - (int)seg_begin, len);
-                        }
-                        seg_begin = seg_end;
-                        ++k;
+                for (uint32_t kk = warp; kk < nstrips; kk += K2_WARPS) {
+                    const uint32_t seg_begin = s_seg_end[kk], len = s_seg_end[kk + 1] - seg_begin;
+                    const uint32_t dstbit = rel_begin + seg_begin, sh = dstbit & 31u, nw = (len + 31u) >> 5;
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(tile_streams + kk * (uint64_t)a.slot_bytes);
+                    uint32_t *dst = win + (dstbit >> 5);
+                    uint32_t carry = 0;                                           // word i-1 for lane 0
+                    for (uint32_t i0 = 0; i0 < nw + 1; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const uint32_t cur_w = i < nw ? src[i] : 0u;
+                        uint32_t prev_w = __shfl_up_sync(0xffffffffu, cur_w, 1);
+                        if (lane == 0) prev_w = carry;
+                        carry = __shfl_sync(0xffffffffu, cur_w, 31);
+                        const uint32_t v = __funnelshift_r(cur_w, prev_w, sh);    // (word i-1 : word i) >> phase
+                        if (v != 0u && i < nw + 1) atomicOr(dst + i, v);
                     }
-                    // the (at most two) strips after the tile, clipped to the bits that complete the last byte
-                    if ((int)tile_bits < P + 32 && succ1) {
-                        acc |= segment_bits(reinterpret_cast<const uint32_t *>(tile_streams + nstrips * (uint64_t)a.slot_bytes), P - (int)tile_bits, succ1);
-                        if (succ2)
-                            acc |= segment_bits(reinterpret_cast<const uint32_t *>(tile_streams + (nstrips + 1) * (uint64_t)a.slot_bytes),
-                                                P - (int)(tile_bits + succ1), succ2);
-                    }
-                    win[j] = acc;
                 }
-                if (tid < 4) win[nwords + tid] = 0;                            // the write-out reads whole 16-byte groups
+                if (tid == 0) {
+                    if (tile == 0) window_put(win, rel_begin, s_pseudo[0]);       // the image's first DC symbol
+                    // the (at most two) strips after the tile, clipped to the bits that complete the last byte
+                    if (succ1) {
+                        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tile_streams + nstrips * (uint64_t)a.slot_bytes);
+                        window_put(win, rel_begin + tile_bits, w1 & (0xFFFFFFFFu << (32u - succ1)));
+                        if (succ2) {
+                            const uint32_t w2 = *reinterpret_cast<const uint32_t *>(tile_streams + (nstrips + 1) * (uint64_t)a.slot_bytes);
+                            window_put(win, rel_begin + tile_bits + succ1, w2 & (0xFFFFFFFFu << (32u - succ2)));
+                        }
+                    }
+                }
             }
             __syncthreads();
 
@@ -294,9 +323,13 @@ k_merge_stuff(const PackArgs a, const int win_words)
             mine.B0 = (begin + 7) >> 3;
             mine.B1 = fits ? (end + 7) >> 3 : mine.B0;
             const uint32_t wb0 = (uint32_t)(mine.B0 - 4 * w0), wb1 = (uint32_t)(mine.B1 - 4 * w0);   // window byte range
-            const uint32_t wfirst = wb0 >> 2, wlast = (wb1 + 3) >> 2;                                // window word range
+            const uint32_t wlast = (wb1 + 3) >> 2;                                                   // window word range
+            mine.nwords = nwords;
             uint32_t ffs = 0;
-            for (uint32_t i = wfirst + tid; i < wlast; i += K2_THREADS) ffs += count_ff_bytes(masked_word(win, i, wb0, wb1));
+            for (uint32_t i = ((wb0 >> 2) & ~3u) + 4u * tid; i < wlast; i += 4u * K2_THREADS) {
+                uint32_t v[4];
+                ffs += masked_quad(win, i, wb0, wb1, v);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ffs += __shfl_xor_sync(0xffffffffu, ffs, o);
             if (lane == 0) s_warp[warp] = ffs;
@@ -343,21 +376,9 @@ k_merge_stuff(const PackArgs a, const int win_words)
             for (uint32_t i0 = (wb0 >> 2) & ~3u; i0 < wlast; i0 += K2_ROUND_WORDS) {
                 const uint32_t i = i0 + 4 * tid;
                 uint32_t v[4];
-                {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(win + i);    // beyond wlast: masked off below
-                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-                }
+                const uint32_t cnt = masked_quad(win, i, wb0, wb1, v);            // beyond wlast: masked off
                 // owned bytes of this thread's group: window bytes [lo, hi)
                 const uint32_t lo = min(max(4u * i, wb0), wb1), hi = max(min(4u * i + 16u, wb1), lo);
-                uint32_t cnt = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t m = v[j];
-                    const uint32_t b = 4u * (i + j);
-                    if (b < lo) m &= lo - b >= 4u ? 0u : 0xFFFFFFFFu >> (8u * (lo - b));
-                    if (b + 4u > hi) m &= hi > b ? 0xFFFFFFFFu << (8u * (b + 4u - hi)) : 0u;
-                    cnt += count_ff_bytes(m);
-                }
                 const uint32_t nb = hi - lo;                                      // owned stream bytes
                 uint32_t incl = (cnt << 16) | nb;                                 // both prefix sums at once (nb, cnt <= 2^15 per round)
 #pragma unroll
@@ -406,6 +427,10 @@ k_merge_stuff(const PackArgs a, const int win_words)
                 }
                 round_pos += round_bytes;
                 __syncthreads();                                                  // staging area and s_warp are reused
+            }
+            {   // the window is handed back zeroed
+                uint4 *wq = reinterpret_cast<uint4 *>(k2_smem_words + (cur ^ 1) * win_words);
+                for (uint32_t i = tid; 4u * i < w.nwords + 4u; i += K2_THREADS) wq[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             K2_TRACE(w.t, 7);
         }
