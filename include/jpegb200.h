@@ -262,7 +262,7 @@ int jpegb200_encoder_read_k1_trace(jpegb200_encoder *enc, uint64_t *host, uint64
 typedef struct {
     int16_t  first_dc;
     int16_t  last_dc;
-    uint32_t reserved;
+    uint32_t reserved;              /* device variants: 1 = the rank owns block rows, 0 = empty slot */
     uint64_t bits_pred0;
 } jpegb200_stripe_summary;
 
@@ -271,6 +271,19 @@ int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int wid
 int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin,
                            uint8_t *d_scan, uint64_t scan_capacity, uint64_t *host_scan_bytes,
                            void *cuda_stream);
+
+/* Device-resident variants: nothing returns to the host between analyze, exchange and encode, so the three steps
+ * can be enqueued back to back on one stream (and captured in a CUDA graph).
+ *   analyze_device : as above, the summary is reduced on the device and written to d_out (device memory, 16 bytes)
+ *   -- all-gather the summaries into d_all[world] on the device (NCCL); a rank without block rows contributes an
+ *      all-zero slot --
+ *   encode_device  : a one-warp kernel derives this rank's predictor and global bit offset from d_all (the device
+ *                    version of stripes.resolve_offsets), then scan + merge + stuff.  d_scan_info[0] = 0,
+ *                    d_scan_info[1] = stuffed bytes this rank produced (device memory). */
+int jpegb200_stripe_analyze_device(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
+                                   int halo_rows, jpegb200_stripe_summary *d_out, void *cuda_stream);
+int jpegb200_stripe_encode_device(jpegb200_encoder *enc, const jpegb200_stripe_summary *d_all, int world, int rank,
+                                  uint8_t *d_scan, uint64_t scan_capacity, uint64_t *d_scan_info, void *cuda_stream);
 
 /* Synthetic workload generator on the device:
  * fills count images of w x h RGB, image i uses seed0 + i. */

@@ -74,7 +74,8 @@ EXPORTED_FUNCTIONS = [
     "jpegb200_encoder_stats", "jpegb200_encoder_read_coefficients", "jpegb200_encoder_read_block_bits", "jpegb200_encoder_read_trace", "jpegb200_encoder_read_k1_trace",
     "jpegb200_encoder_set_profiling", "jpegb200_encoder_kernel_times", "jpegb200_encode_host",
     "jpegb200_encode_bmp_to_jpeg_host",
-    "jpegb200_stripe_analyze", "jpegb200_stripe_encode", "jpegb200_synth_rgb_device",
+    "jpegb200_stripe_analyze", "jpegb200_stripe_encode", "jpegb200_stripe_analyze_device", "jpegb200_stripe_encode_device",
+    "jpegb200_synth_rgb_device",
 ]
 EXPORTED_DATA = ["std_luminance_quant_tbl", "std_dc_luminance_nrcodes", "std_dc_luminance_values",
                  "std_ac_luminance_nrcodes", "std_ac_luminance_values"]
@@ -144,6 +145,8 @@ def load_library():
     L.jpegb200_encode_bmp_to_jpeg_host.argtypes = [vp, vp, u64, vp, u64, P(u64), P(C.c_int), P(C.c_int), vp]
     L.jpegb200_stripe_analyze.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, P(StripeSummary), vp]
     L.jpegb200_stripe_encode.argtypes = [vp, C.c_int16, u64, vp, u64, P(u64), vp]
+    L.jpegb200_stripe_analyze_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.jpegb200_stripe_encode_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, u64, vp, vp]
     L.jpegb200_synth_rgb_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64, C.c_uint32, C.c_int, vp]
     _lib = L
     return L

@@ -258,7 +258,6 @@ static int upload_tables(jpegb200_encoder *enc)
     return JPEGB200_OK;
 }
 
-// misc layout: [0] uint32 err, [8] uint64 flagged counter, [16..] stripe scratch
 static uint32_t *misc_err(jpegb200_encoder *e) { return reinterpret_cast<uint32_t *>(e->misc.ptr); }
 static unsigned long long *misc_flagged(jpegb200_encoder *e)
 {
@@ -812,10 +811,15 @@ extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t 
 
 // ---- C ABI: MCU-row stripes -------------------------------------------------------------
 
-extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
-                                       int halo_rows, jpegb200_stripe_summary *host_out, void *cuda_stream)
+// misc layout (256 bytes): [0] uint32 err, [8] uint64 flagged counter, [16] uint64[2] scan offsets,
+// [64] stripe summary (16 bytes), [96] StripeDyn (24 bytes)
+static StripeSummaryDev *misc_summary(jpegb200_encoder *e) { return reinterpret_cast<StripeSummaryDev *>(static_cast<uint8_t *>(e->misc.ptr) + 64); }
+static StripeDyn *misc_dyn(jpegb200_encoder *e) { return reinterpret_cast<StripeDyn *>(static_cast<uint8_t *>(e->misc.ptr) + 96); }
+
+extern "C" int jpegb200_stripe_analyze_device(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
+                                              int halo_rows, jpegb200_stripe_summary *d_out, void *cuda_stream)
 {
-    if (!host_out) return JPEGB200_ERR_ARG;
+    if (!d_out) return JPEGB200_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int rc = prepare(enc, d_rgb, width, stripe_height, 1, 0, halo_rows);
     if (rc) return rc;
@@ -823,17 +827,53 @@ extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_r
     if ((rc = launch_block_kernel(enc, st))) return rc;
     if ((rc = launch_strip_entropy(enc, st, enc->want_taps))) return rc;
     const PackArgs &a = enc->args;
-    std::vector<StripRec> recs(a.strips_owned);
-    JB_CUDA(cudaMemcpyAsync(recs.data(), a.strips, recs.size() * sizeof(StripRec), cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    uint64_t bits = enc->tables.dc_len[bit_length((int)recs.front().first_dc)];   // first DC symbol, predictor 0
-    for (const StripRec &r : recs) bits += r.bits;
-    host_out->first_dc = recs.front().first_dc;
-    host_out->last_dc = recs.back().last_dc;
-    host_out->reserved = 0;
-    host_out->bits_pred0 = bits;
+    ++enc->launches;
+    k_stripe_summary<<<1, 256, 0, st>>>(a.strips, a.strip_bits, a.strips_owned, reinterpret_cast<StripeSummaryDev *>(d_out));
+    JB_CUDA(cudaGetLastError());
     enc->stripe_ready = true;
     return JPEGB200_OK;
+}
+
+extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
+                                       int halo_rows, jpegb200_stripe_summary *host_out, void *cuda_stream)
+{
+    if (!enc || !host_out) return JPEGB200_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int rc = jpegb200_stripe_analyze_device(enc, d_rgb, width, stripe_height, halo_rows,
+                                            reinterpret_cast<jpegb200_stripe_summary *>(misc_summary(enc)), cuda_stream);
+    if (rc) return rc;
+    JB_CUDA(cudaMemcpyAsync(host_out, misc_summary(enc), sizeof(jpegb200_stripe_summary), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    return JPEGB200_OK;
+}
+
+// K2 for a stripe; dyn == nullptr: predictor and phase come from enc->args (host values)
+static int stripe_encode_launch(jpegb200_encoder *enc, const StripeDyn *dyn, uint8_t *d_scan, uint64_t scan_capacity, uint64_t *d_scan_info,
+                                cudaStream_t st)
+{
+    PackArgs &a = enc->args;
+    a.dyn = dyn;
+    a.out = d_scan;
+    a.out_capacity = scan_capacity;
+    a.out_slot = 0;
+    a.scan_offsets = d_scan_info;
+    JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));   // idempotent re-runs
+    return launch_entropy(enc, st);
+}
+
+extern "C" int jpegb200_stripe_encode_device(jpegb200_encoder *enc, const jpegb200_stripe_summary *d_all, int world, int rank,
+                                             uint8_t *d_scan, uint64_t scan_capacity, uint64_t *d_scan_info, void *cuda_stream)
+{
+    if (!enc || !d_all || !d_scan || !d_scan_info || world <= 0 || rank < 0 || rank >= world || !enc->stripe_ready) {
+        g_last_error = "jpegb200_stripe_encode_device: bad argument, or no preceding jpegb200_stripe_analyze";
+        return JPEGB200_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    JB_CUDA(cudaSetDevice(enc->device));
+    ++enc->launches;
+    k_stripe_resolve<<<1, 32, 0, st>>>(reinterpret_cast<const StripeSummaryDev *>(d_all), rank, misc_dyn(enc));
+    JB_CUDA(cudaGetLastError());
+    return stripe_encode_launch(enc, misc_dyn(enc), d_scan, scan_capacity, d_scan_info, st);
 }
 
 extern "C" int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin, uint8_t *d_scan,
@@ -845,16 +885,10 @@ extern "C" int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predicto
     }
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     JB_CUDA(cudaSetDevice(enc->device));
-    PackArgs &a = enc->args;
-    a.dc_pred0 = dc_predictor;
-    a.bit_phase = (uint32_t)(bit_begin & 7u);
-    a.out = d_scan;
-    a.out_capacity = scan_capacity;
-    a.out_slot = 0;
-    a.scan_offsets = misc_offsets(enc);
-    JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));   // idempotent re-runs
-    int rc = 0;
-    if ((rc = launch_entropy(enc, st))) return rc;
+    enc->args.dc_pred0 = dc_predictor;
+    enc->args.bit_phase = (uint32_t)(bit_begin & 7u);
+    int rc = stripe_encode_launch(enc, nullptr, d_scan, scan_capacity, misc_offsets(enc), st);
+    if (rc) return rc;
     uint64_t offs[2] = {0, 0};
     JB_CUDA(cudaMemcpyAsync(offs, misc_offsets(enc), 16, cudaMemcpyDeviceToHost, st));
     JB_CUDA(cudaStreamSynchronize(st));

@@ -442,6 +442,58 @@ k_merge_stuff(const PackArgs a, const int win_words)
 }
 
 // ---------------------------------------------------------------------------------
+// stripes: boundary summary of one stripe, reduced on the device (one CTA).  bits_pred0 = the stripe's bit count if
+// its first block were predicted from DC 0 (the strips' counts lack exactly that one symbol).
+struct StripeSummaryDev {        // = jpegb200_stripe_summary
+    int16_t first_dc;
+    int16_t last_dc;
+    uint32_t valid;              // 1: the rank owns block rows; 0: empty slot
+    uint64_t bits_pred0;
+};
+
+__global__ void __launch_bounds__(256)
+k_stripe_summary(const StripRec *__restrict__ strips, const uint32_t *__restrict__ strip_bits, const uint32_t strips_owned,
+                 StripeSummaryDev *__restrict__ out)
+{
+    __shared__ uint64_t s_part[8];
+    uint64_t sum = 0;
+    for (uint32_t i = threadIdx.x; i < strips_owned; i += 256) sum += strip_bits[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t bits = 0;
+        for (int w = 0; w < 8; ++w) bits += s_part[w];
+        const int first_dc = strips[0].first_dc;
+        bits += c_dc_len[magnitude_class_k2(first_dc)];           // first DC symbol, predictor 0 (rle.c:68-76)
+        out->first_dc = (int16_t)first_dc;
+        out->last_dc = strips[strips_owned - 1].last_dc;
+        out->valid = 1u;
+        out->bits_pred0 = bits;
+    }
+}
+
+// stripes: from all ranks' summaries derive this rank's DC predictor and global bit offset (the device version of
+// stripes.resolve_offsets): the true cost of a stripe's first DC symbol replaces the predictor-0 cost.
+__global__ void k_stripe_resolve(const StripeSummaryDev *__restrict__ all, const int rank, StripeDyn *__restrict__ dyn)
+{
+    if (threadIdx.x != 0) return;
+    uint64_t bit = 0;
+    int pred = 0;
+    for (int r = 0; r < rank; ++r) {
+        if (!all[r].valid) continue;
+        const int fd = all[r].first_dc;
+        bit += all[r].bits_pred0 - c_dc_len[magnitude_class_k2(fd)] + c_dc_len[magnitude_class_k2(fd - pred)];
+        pred = all[r].last_dc;
+    }
+    dyn->dc_pred0 = pred;
+    dyn->bit_phase = (uint32_t)(bit & 7u);
+    dyn->bit_begin = bit;
+    dyn->byte_begin = (bit + 7) >> 3;
+}
+
+// ---------------------------------------------------------------------------------
 // batch mode: exclusive scan of the stuffed image sizes -> scan_offsets[count+1]  (one CTA)
 // `extra`: bytes that frame every image in the output besides its scan (0, or 330 in files mode: the
 // 328-byte JFIF header and the 2-byte EOI marker)

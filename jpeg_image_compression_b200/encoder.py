@@ -180,6 +180,18 @@ class DeviceEncoder:
                                               C.byref(n), self._stream()), "stripe_encode")
         return int(n.value)
 
+    def stripe_analyze_device(self, d_rgb, w: int, stripe_h: int, halo_rows: int, d_summary):
+        """Like stripe_analyze, but the 16-byte summary stays on the device (d_summary: int64[2] CUDA tensor or a
+        slice of the all-gather buffer).  Asynchronous on the current stream."""
+        check(self.lib.jpegb200_stripe_analyze_device(self.handle, d_rgb.data_ptr(), w, stripe_h, halo_rows,
+                                                      d_summary.data_ptr(), self._stream()), "stripe_analyze_device")
+
+    def stripe_encode_device(self, d_all, world: int, rank: int, scan, d_info):
+        """Resolve this rank's predictor / bit offset from all ranks' summaries (d_all: int64[world, 2] on the
+        device) and run the merge kernel; d_info (int64[2] on the device) receives [0, stuffed bytes]."""
+        check(self.lib.jpegb200_stripe_encode_device(self.handle, d_all.data_ptr(), world, rank, scan.data_ptr(), scan.numel(),
+                                                     d_info.data_ptr(), self._stream()), "stripe_encode_device")
+
     # ---- synthetic inputs on the device --------------------------------------------
     def synth(self, w: int, h: int, count: int = 1, seed0: int = 1, amp: int = 20):
         t = self.torch

@@ -149,6 +149,55 @@ class StripedEncoder:
             return 0
         return self.backend.stripe_encode(mine[0], mine[1], scan)
 
+    def encode_on_device(self, stripe, width: int, height: int, scan, summaries=None, info=None):
+        """The same encode with no host round trip between analyze, exchange and merge (CUDA backends only):
+        the boundary summaries are reduced on the device, all-gathered as device tensors (NCCL) and resolved by a
+        one-warp kernel.  Returns `info`, an int64[2] device tensor whose element 1 is this rank's stuffed byte count
+        (read it after synchronising)."""
+        import torch
+        dev = scan.device
+        if summaries is None:
+            summaries = torch.zeros((self.world, 2), dtype=torch.int64, device=dev)
+        if info is None:
+            info = torch.zeros(2, dtype=torch.int64, device=dev)
+        mine = torch.zeros(2, dtype=torch.int64, device=dev)
+        _, owned, halo = stripe_rows(height, self.world, self.rank)
+        if owned:
+            self.backend.stripe_analyze_device(stripe, width, owned, halo, mine)
+        self.dist.all_gather_into_tensor(summaries.view(-1), mine, group=self.group)
+        if owned:
+            self.backend.stripe_encode_device(summaries, self.world, self.rank, scan, info)
+        else:
+            info.zero_()
+        return info
+
+    def gather_exact(self, scan, nbytes_dev, out=None):
+        """Stitch on rank 0 with size-exact transfers: sizes are all-gathered on the device (one host read), then
+        every rank sends exactly its bytes and rank 0 receives them at their offsets.  Returns (tensor, total) on
+        rank 0, (None, total) elsewhere."""
+        import torch
+        dev = scan.device
+        sizes_d = torch.empty(self.world, dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(sizes_d, nbytes_dev.reshape(1), group=self.group)
+        sizes = sizes_d.tolist()                                  # the one host synchronisation of the striped encode
+        total = int(sum(sizes))
+        if self.rank == 0:
+            if out is None or out.numel() < total:
+                out = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+            if sizes[0]:
+                out[: sizes[0]].copy_(scan[: sizes[0]])
+            reqs, off = [], sizes[0]
+            for r in range(1, self.world):
+                if sizes[r]:
+                    reqs.append(self.dist.irecv(out[off: off + sizes[r]], src=r, group=self.group))
+                off += sizes[r]
+            for q in reqs:
+                q.wait()
+            return out, total
+        if sizes[self.rank]:
+            self.dist.send(scan[: sizes[self.rank]], dst=0, group=self.group)
+        return None, total
+
     def gather(self, scan, nbytes: int) -> Optional[bytes]:
         """Stitch: every rank's stuffed bytes, in rank order, on rank 0 (None elsewhere)."""
         import torch

@@ -138,6 +138,21 @@ def main() -> None:
             "symbols": int(st["symbols"].size),
         }
         print(w, h, seed, amp, len(st["scan"]), st["symbols"].size, flush=True)
+    # BASELINE config 5 is beyond the reference's int-indexed buffers: minted by the oracle's streaming twin
+    big = orc.encode_scan_synth_banded(32768, 32768, 1, 20, 8, 0)
+    hashes["32768x32768_seed1_amp20"] = {
+        "w": 32768, "h": 32768, "seed": 1, "amp": 20, "scan_bytes": len(big), "scan_sha256": sha(big),
+        "minted_by": "oracle streaming (banded) encode, orc_encode_scan_synth_banded: the stock reference cannot hold this "
+                     "image (int-indexed buffers, SURVEY.md 7.3-F)"}
+    del big
+    # the -O2 reference twin must equal the reference built at its own flags (natural_c/Makefile:4, -g)
+    ref_g_path = os.path.join(os.path.dirname(HERE), "..", "oracle", "_ref", "libnaturalc_ref_g.so")
+    if os.path.exists(ref_g_path):
+        ref_g = Ref(os.path.abspath(ref_g_path))
+        for (w, h, seed, amp) in [(640, 360, 3, 20), (257, 131, 4, 64)]:
+            rgb = orc.synth_rgb(w, h, seed, amp)
+            a, b = ref.stages(rgb), ref_g.stages(rgb)
+            assert bytes(a["scan"]) == bytes(b["scan"]) and np.array_equal(a["zigzag"], b["zigzag"]), "-O2 twin differs from the stock -g build"
     # the four reference assets (inputs are not committed; hashes are checked when
     # /root/reference is present, i.e. in the build container)
     for name in ["lena", "blackbuck", "greenland", "offset_sample"]:

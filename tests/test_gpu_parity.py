@@ -285,6 +285,52 @@ def test_cli_end_to_end(golden, tmp_path, ref):
             assert open(out_ref, "rb").read() == open(out, "rb").read()
 
 
+def test_reference_orchestrator_over_library(golden, tmp_path):
+    """INTEGRATION.md option A, executed: the reference's UNMODIFIED main.c + src/io/bmp_handler.c + src/io/jpeg_handler.c
+    (saveJPEGGrayscale, natural_c/src/io/jpeg_handler.c:119-282) linked against libjpegb200.so instead of its own
+    src/core/*.c -- the seven stage calls at jpeg_handler.c:133-201 run as CUDA kernels.  File bytes and stdout must
+    equal those of the reference binary."""
+    from oracle.oracle import REF_APP, write_bmp
+    app = os.path.join(ROOT, "oracle", "_ref", "jpeg_compression_app_optA")
+    if not os.path.exists(app):
+        pytest.skip("oracle/_ref/jpeg_compression_app_optA not built (needs /root/reference at build time)")
+    for name in ["lena_crop256", "greenland_corner250x205", "one_pixel"]:
+        rgb = golden[f"{name}/rgb"]
+        bmp, out, out_ref = (str(tmp_path / f"{name}{s}") for s in (".bmp", "_a.jpg", "_ref.jpg"))
+        write_bmp(bmp, rgb)
+        r = subprocess.run([app, bmp, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == golden[f"{name}/file"].tobytes(), name
+        if os.path.exists(REF_APP):
+            rr = subprocess.run([REF_APP, bmp, out_ref], capture_output=True, text=True)
+            assert rr.stdout.replace(out_ref, "X") == r.stdout.replace(out, "X"), name
+    # the library in use really is ours: the binary has no core stage of its own
+    syms = subprocess.run(["nm", "-D", "--undefined-only", app], capture_output=True, text=True).stdout
+    for fn in ("convertBMPToJPEGGrayscale", "centerYImage", "performDCT", "quantizeImage", "performZigZag", "performRLE", "encodeHuffman"):
+        assert fn in syms, fn
+
+
+def test_full_size_assets(enc, synth_hashes, tmp_path):
+    """BASELINE configs[0]: the reference's own assets/input/*.bmp at full size (copied next to oracle/_ref by build();
+    not committed), through the BMP loader + fused path and through the in-place BMP ingest, against the hashes minted
+    from the reference build."""
+    adir = os.path.join(ROOT, "oracle", "_ref", "assets")
+    names = [n for n in ("lena", "blackbuck", "greenland", "offset_sample") if os.path.exists(os.path.join(adir, n + ".bmp"))]
+    if not names:
+        pytest.skip("asset BMPs not present (oracle/_ref/assets)")
+    app = os.path.join(ROOT, "jpeg_image_compression_b200", "jpeg_compression_app")
+    for name in names:
+        e = synth_hashes["asset_" + name]
+        path = os.path.join(adir, name + ".bmp")
+        out = str(tmp_path / (name + ".jpg"))
+        r = subprocess.run([app, path, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        data = open(out, "rb").read()
+        scan = data[328:-2]
+        assert len(scan) == e["scan_bytes"] and hashlib.sha256(scan).hexdigest() == e["scan_sha256"], name
+        assert enc.encode_bmp_to_jpeg(open(path, "rb").read()) == data, name
+
+
 # ---- MCU-row stripes (several ranks emulated on one GPU: one encoder handle per rank) ------------
 
 def _striped_on_one_gpu(encoders, rgb_t, w, h):
@@ -329,6 +375,50 @@ def test_stripes_8k_hash(rank_encoders, enc, synth_hashes):
     for world in (2, 4, 8):
         got = _striped_on_one_gpu(rank_encoders[:world], d, e["w"], e["h"])
         assert len(got) == e["scan_bytes"] and hashlib.sha256(got).hexdigest() == e["scan_sha256"], world
+
+
+def _striped_on_one_gpu_device_path(encoders, rgb_t, w, h):
+    """The device-resident stripe path: summaries reduced and resolved by kernels, nothing returns to the host
+    between analyze, the (here: emulated) all-gather and the merge."""
+    import torch
+    from jpeg_image_compression_b200.stripes import stripe_rows
+    world = len(encoders)
+    summaries = torch.zeros((world, 2), dtype=torch.int64, device="cuda")      # the all-gather buffer
+    infos = torch.zeros((world, 2), dtype=torch.int64, device="cuda")
+    stripes, scans = [], []
+    for r in range(world):
+        y0, owned, halo = stripe_rows(h, world, r)
+        stripes.append(rgb_t[y0:y0 + owned + halo].contiguous())
+        scans.append(torch.empty(encoders[0].scan_capacity(w, max(owned, 8), 1), dtype=torch.uint8, device="cuda"))
+        if owned:
+            encoders[r].stripe_analyze_device(stripes[r], w, owned, halo, summaries[r])
+    for r in range(world):
+        if stripe_rows(h, world, r)[1]:
+            encoders[r].stripe_encode_device(summaries, world, r, scans[r], infos[r])
+    torch.cuda.synchronize()
+    for e in encoders:
+        e.status()
+    sizes = infos[:, 1].tolist()
+    return b"".join(scans[r][: sizes[r]].cpu().numpy().tobytes() for r in range(world))
+
+
+def test_stripes_device_path(rank_encoders, enc, oracle, synth_hashes):
+    import torch
+    rng = np.random.default_rng(9)
+    for (w, h, world, kind) in [(64, 64, 2, "synth"), (70, 45, 2, "noise"), (200, 37, 4, "synth"), (16, 9, 4, "noise"),
+                                (40, 24, 3, "flat"), (1283, 725, 8, "synth")]:
+        if kind == "synth":
+            rgb = oracle.synth_rgb(w, h, 3, 25)
+        elif kind == "noise":
+            rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        else:
+            rgb = np.full((h, w, 3), 77, np.uint8)
+        got = _striped_on_one_gpu_device_path(rank_encoders[:world], torch.from_numpy(rgb).cuda(), w, h)
+        assert got == oracle.encode_scan(rgb), (w, h, world, kind)
+    e = synth_hashes["7680x4320_seed1_amp20"]
+    d = enc.synth(e["w"], e["h"], 1, e["seed"], e["amp"])[0]
+    got = _striped_on_one_gpu_device_path(rank_encoders[:8], d, e["w"], e["h"])
+    assert len(got) == e["scan_bytes"] and hashlib.sha256(got).hexdigest() == e["scan_sha256"]
 
 
 def test_dense_tiles_and_ff_bytes(enc, oracle):
