@@ -607,6 +607,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                         "timed": "analyze + all-gather of the boundary summaries + merge (device-resident, no host round trip)"
                         if world > 1 else "single-GPU encode"})
             if world > 1:
+                gather()                                      # first use sets up the NCCL point-to-point connections
                 sync_all()
                 t0 = time.perf_counter()
                 stitched, total = gather()

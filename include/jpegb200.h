@@ -242,6 +242,8 @@ int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t 
 /* Same for the block kernel (JPEGB200_K1_TRACE=1): 8 timestamps per persistent warp, followed (pass
  * 2 x the warp count) by the completion times of each warp's first 8 strips. */
 int jpegb200_encoder_read_k1_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t nwarps);
+/* Grid and warps per CTA of the last block-kernel launch (sizes the trace above). */
+int jpegb200_encoder_launch_shape(jpegb200_encoder *enc, int *k1_grid, int *k1_warps_per_cta);
 
 /* ---- MCU-row stripes of one image across several GPUs ----------------------
  * Rank r owns block rows [row0, row0+rows) of an image.  d_rgb points at the stripe's first

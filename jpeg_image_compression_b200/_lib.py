@@ -71,7 +71,7 @@ EXPORTED_FUNCTIONS = [
     "jpegb200_encode_scan", "jpegb200_encode_scan_dbg", "jpegb200_jfif_header", "jpegb200_device_count",
     "jpegb200_last_error", "jpegb200_encoder_create", "jpegb200_encoder_destroy", "jpegb200_encoder_set_dct_mode",
     "jpegb200_encoder_set_bytes_per_block", "jpegb200_encode_batch_device", "jpegb200_encode_batch_files_device", "jpegb200_encoder_status",
-    "jpegb200_encoder_stats", "jpegb200_encoder_read_coefficients", "jpegb200_encoder_read_block_bits", "jpegb200_encoder_read_trace", "jpegb200_encoder_read_k1_trace",
+    "jpegb200_encoder_stats", "jpegb200_encoder_read_coefficients", "jpegb200_encoder_read_block_bits", "jpegb200_encoder_read_trace", "jpegb200_encoder_read_k1_trace", "jpegb200_encoder_launch_shape",
     "jpegb200_encoder_set_profiling", "jpegb200_encoder_kernel_times", "jpegb200_encode_host",
     "jpegb200_encode_bmp_to_jpeg_host",
     "jpegb200_stripe_analyze", "jpegb200_stripe_encode", "jpegb200_stripe_analyze_device", "jpegb200_stripe_encode_device",
@@ -139,6 +139,7 @@ def load_library():
     L.jpegb200_encoder_read_block_bits.argtypes = [vp, vp, u64]
     L.jpegb200_encoder_read_trace.argtypes = [vp, vp, u64]
     L.jpegb200_encoder_read_k1_trace.argtypes = [vp, vp, u64]
+    L.jpegb200_encoder_launch_shape.argtypes = [vp, P(C.c_int), P(C.c_int)]
     L.jpegb200_encoder_set_profiling.argtypes = [vp, C.c_int]
     L.jpegb200_encoder_kernel_times.argtypes = [vp, P(C.c_double), P(u64), C.c_int]
     L.jpegb200_encode_host.argtypes = [vp, vp, C.c_int, C.c_int, vp, u64, P(u64), vp]

@@ -191,26 +191,33 @@ __device__ __forceinline__ float u8_to_centered(uint32_t word, int byte)
     return __uint_as_float(bits) - 8388736.0f;
 }
 
-// Reference-order evaluation of ONE quantized coefficient (dct.c:65-93,
-// quantization.c:34-36): sequential fp32 sum, two unfused multiplies per term, IEEE
-// divide, round half away from zero.  yblk: the block's Y bytes (pitch Y_PITCH).
-__device__ __noinline__ int exact_quantized(const uint8_t *yblk, int u, int v)
+// Reference-order evaluation of ONE quantized coefficient (dct.c:65-93, quantization.c:34-36): sequential fp32 sum of
+// 64 products, two unfused multiplies per term, IEEE divide, round half away from zero.  Warp-cooperative: every lane
+// forms two of the 64 products fl(fl(p * cos[r][u]) * cos[c][v]) -- they are independent -- and parks them in the
+// warp's scratch; only the ordered summation is serial, done by the lane that owns the block (the other lanes of
+// the warp, and through the tile barrier its three sibling warps, wait for it: a single-lane evaluation of all 64
+// terms took four times as long).  yblk: the block's Y bytes (pitch Y_PITCH); scratch: 64 floats, 16-byte aligned.
+// Must be called by the whole warp with uniform (yblk, u, v); returns the quantized value (valid on every lane).
+__device__ __forceinline__ int exact_quantized_coop(const uint8_t *yblk, int u, int v, const float *s_cos, float *scratch, int lane)
 {
-    float cv[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) cv[c] = c_ref_cos[c * 8 + v];
+    const int r = lane >> 2, c = 2 * (lane & 3);
+    const float cu = s_cos[r * 8 + u];
+    const uint32_t two = *reinterpret_cast<const uint16_t *>(yblk + r * Y_PITCH + c);
+    const float p0 = (float)((int)(two & 0xFFu) - 128), p1 = (float)((int)(two >> 8) - 128);     // converter.c:84
+    const float t0 = __fmul_rn(__fmul_rn(p0, cu), s_cos[c * 8 + v]);
+    const float t1 = __fmul_rn(__fmul_rn(p1, cu), s_cos[(c + 1) * 8 + v]);
+    *reinterpret_cast<float2 *>(scratch + 2 * lane) = make_float2(t0, t1);
+    __syncwarp();
     float acc = 0.0f;
-#pragma unroll 1
-    for (int r = 0; r < 8; ++r) {
-        const float cu = c_ref_cos[r * 8 + u];
-        const uint2 w = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float t = __fmul_rn(u8_to_centered(c < 4 ? w.x : w.y, c & 3), cu);
-            t = __fmul_rn(t, cv[c]);
-            acc = __fadd_rn(acc, t);
-        }
+    for (int i = 0; i < 16; ++i) {
+        const float4 t = *reinterpret_cast<const float4 *>(scratch + 4 * i);       // same address on every lane: broadcast
+        acc = __fadd_rn(acc, t.x);
+        acc = __fadd_rn(acc, t.y);
+        acc = __fadd_rn(acc, t.z);
+        acc = __fadd_rn(acc, t.w);
     }
+    __syncwarp();
     const float f = __fmul_rn(c_ref_scale[u * 8 + v], acc);
     return (int)roundf(__fdiv_rn(f, c_quant_f[u * 8 + v]));
 }
@@ -332,6 +339,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     uint8_t *ybuf = raw + RAW_BYTES;
     __shared__ __align__(8) uint64_t s_bar[WARPS + 1 + 4];       // per-warp tile barriers, the table barrier, per-group MMA barriers
     __shared__ uint32_t s_tmem;
+    __shared__ float s_cos[64];                                  // the reference's cosine LUT (exact re-evaluation)
+    __shared__ __align__(16) float s_scratch[WARPS][64];         // per warp: the 64 products of one re-evaluated coefficient
 
     K1_TRACE(0);
     // Static schedule.  TC: a group of four warps takes tiles of four consecutive strips, tile = group index, + number of
@@ -349,6 +358,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
         if (TC)
             for (int i = 0; i < Cfg::GROUPS; ++i) mbar_init(&s_bar[WARPS + 1 + i], 1);
     }
+    if (threadIdx.x < 64) s_cos[threadIdx.x] = c_ref_cos[threadIdx.x];
     mbar_fence_init();
     if (TC && warp == 0) tmem_alloc(&s_tmem, Cfg::TMEM_COLS);
     if (TC) tc_fence_before_sync();
@@ -606,32 +616,45 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
         }
         if (!valid) continue;                                    // (TC only) idle warp of the last tile: barriers done
 
+        uint32_t anyx = 0;
         if (lane < me.vb) {
             // DC: exact integer sum in all formulations; reference operation sequence
             // fl(k00 * S) / 16 then roundf (dct.c:93, quantization.c:36)
-            {
-                const float f = __fmul_rn(c_ref_scale[0], x00);
-                const int dcq = (int)roundf(f * 0.0625f);
-                zw[0] = (zw[0] & 0xFFFFFF00u) | ((uint32_t)dcq & 0xFFu);
-                xw[0] &= 0xFFFFFF00u;
-            }
-            uint32_t anyx = 0;
+            const float f = __fmul_rn(c_ref_scale[0], x00);
+            const int dcq = (int)roundf(f * 0.0625f);
+            zw[0] = (zw[0] & 0xFFFFFF00u) | ((uint32_t)dcq & 0xFFu);
+            xw[0] &= 0xFFFFFF00u;
 #pragma unroll
             for (int w = 0; w < 16; ++w) anyx |= xw[w];
-            if (anyx) {
-                // rare (about 1 block in 200): the bracket straddles a rounding boundary for some
-                // coefficient(s); re-evaluate exactly those in the reference's operation order
-                uint64_t fm = 0;
+        }
+        // rare (about 1 block in 200): the bracket straddles a rounding boundary for some coefficient(s); those are
+        // re-evaluated in the reference's operation order, one after the other, by the whole warp
+#ifdef JB_EXPERIMENT_NOFLAG      // timing experiment only (wrong results): how much do the re-evaluations cost?
+        anyx = 0;
+#endif
+        uint32_t pending = __ballot_sync(0xffffffffu, anyx != 0u);
+        while (pending) {
+            const int owner = __ffs((int)pending) - 1;
+            pending &= pending - 1;
+            uint32_t fm_lo = 0, fm_hi = 0;                       // the owner's 64-bit mask of flagged positions
+            if (lane == owner) {
 #pragma unroll
-                for (int w = 0; w < 16; ++w) {
-                    fm |= (uint64_t)nonzero_nibble(xw[w]) << (4 * w);
+                for (int w = 0; w < 8; ++w) {
+                    fm_lo |= nonzero_nibble(xw[w]) << (4 * w);
+                    fm_hi |= nonzero_nibble(xw[w + 8]) << (4 * w);
                 }
+            }
+            fm_lo = __shfl_sync(0xffffffffu, fm_lo, owner);
+            fm_hi = __shfl_sync(0xffffffffu, fm_hi, owner);
+            const uint8_t *oblk = ybuf + owner * 8;
 #pragma unroll 1
-                while (fm) {
-                    const int k = __ffsll((long long)fm) - 1;
-                    fm &= fm - 1;
-                    const int zpos = c_zigzag[k];
-                    const uint32_t q = (uint32_t)exact_quantized(yblk, zpos >> 3, zpos & 7) & 0xFFu;
+            while (fm_lo | fm_hi) {
+                const int k = fm_lo ? __ffs((int)fm_lo) - 1 : 32 + __ffs((int)fm_hi) - 1;
+                if (fm_lo) fm_lo &= fm_lo - 1;
+                else fm_hi &= fm_hi - 1;
+                const int zpos = c_zigzag[k];
+                const uint32_t q = (uint32_t)exact_quantized_coop(oblk, zpos >> 3, zpos & 7, s_cos, s_scratch[warp], lane) & 0xFFu;
+                if (lane == owner) {
                     const uint32_t sh = 8u * (uint32_t)(k & 3), keep = ~(0xFFu << sh), ins = q << sh;
                     const int kw = k >> 2;
 #pragma unroll
@@ -640,6 +663,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                     ++nflag;
                 }
             }
+        }
+        if (lane < me.vb) {
             uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 64);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);

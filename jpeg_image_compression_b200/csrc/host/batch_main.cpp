@@ -81,7 +81,7 @@ int main(int argc, char **argv)
             fclose(f);
             uint64_t bytes = 0;
             int w = 0, h = 0, rc = JPEGB200_ERR_ARG;
-            for (int attempt = 0; ok && attempt < 2; ++attempt) {
+            for (int attempt = 0; ok && attempt < 4; ++attempt) {       // WORKSPACE may be followed by OUTPUT: loop until neither
                 rc = jpegb200_encode_bmp_to_jpeg_host(enc, in.p, (uint64_t)n, out.p, out.n, &bytes, &w, &h, st);
                 if (rc == JPEGB200_ERR_WORKSPACE) jpegb200_encoder_set_bytes_per_block(enc, 184);   // very dense image
                 else if (rc == JPEGB200_ERR_OUTPUT) ok = out.reserve(out.n * 4);

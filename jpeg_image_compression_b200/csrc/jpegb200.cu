@@ -770,6 +770,15 @@ extern "C" int jpegb200_encoder_read_k1_trace(jpegb200_encoder *enc, uint64_t *h
     return JPEGB200_OK;
 }
 
+// shape of the last block-kernel launch (tuning aids)
+extern "C" int jpegb200_encoder_launch_shape(jpegb200_encoder *enc, int *k1_grid, int *k1_warps_per_cta)
+{
+    if (!enc || !k1_grid || !k1_warps_per_cta) return JPEGB200_ERR_ARG;
+    *k1_grid = enc->k1_grid;
+    *k1_warps_per_cta = enc->k1_warps;
+    return JPEGB200_OK;
+}
+
 extern "C" int jpegb200_encoder_read_trace(jpegb200_encoder *enc, uint64_t *host, uint64_t ntiles)
 {
     if (!enc || !host || !enc->trace.ptr || ntiles * 64 > enc->trace.bytes) return JPEGB200_ERR_ARG;

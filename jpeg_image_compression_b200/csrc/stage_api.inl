@@ -295,7 +295,6 @@ extern "C" JpegEncoderBuffer *encodeHuffman(const RLEData *rle, int totalBlocks)
             k_hs_walk<<<wg, 128>>>(d_sym, nsym, d_entry, d_cblk, d_cbit, (uint64_t)totalBlocks, nullptr, d_packed, 2);
             EntropyArgs a{};
             a.image_bits = d_misc;
-            a.image_ff = d_misc + 1;
             a.scan_offsets = d_misc + 2;
             a.packed = d_packed;
             a.packed_capacity = (nbytes / 4 + 8) * 4;
@@ -303,10 +302,8 @@ extern "C" JpegEncoderBuffer *encodeHuffman(const RLEData *rle, int totalBlocks)
             a.scan = d_scan;
             a.scan_capacity = 2 * nbytes + 16;
             a.err = d_err;
-            a.chunks_cap = chunks;
-            a.count = 1;
             a.epoch = 1;
-            k_stuff<<<dim3((unsigned)chunks, 1), K4_THREADS>>>(a, StuffArgs{0, 0, 0});
+            k_stuff<<<(unsigned)chunks, K4_THREADS>>>(a);
             uint64_t offs[2] = {0, 0};
             uint32_t err = 0;
             ok = finish("huffman pack/stuff") && cuda_ok(cudaMemcpy(offs, d_misc + 2, 16, cudaMemcpyDeviceToHost), "D2H") &&

@@ -106,13 +106,27 @@ class DeviceEncoder:
         scans = self.encode_batch(rgb[None])
         return scans[0]
 
+    def _grow_workspace(self):
+        """A dense image overflowed the packed-bits workspace or the scan buffer sized from bytes_per_block: switch to
+        the worst case (184 bytes per block covers every input), like the C entries jpegb200_encode_scan / the batch CLI."""
+        self.bytes_per_block = 184
+        check(self.lib.jpegb200_encoder_set_bytes_per_block(self.handle, 184), "set_bytes_per_block")
+        self._scan = None
+
     def encode_batch(self, rgbs: np.ndarray) -> list:
         t = self.torch
         rgbs = np.ascontiguousarray(rgbs, np.uint8)
         n, h, w, _ = rgbs.shape
         d = t.from_numpy(rgbs).to(f"cuda:{self.device}")
         scan, offsets = self.encode_device(d, w, h, n)
-        self.status()
+        try:
+            self.status()
+        except _lib.JpegB200Error:
+            if self.bytes_per_block >= 184:
+                raise
+            self._grow_workspace()
+            scan, offsets = self.encode_device(d, w, h, n)
+            self.status()
         offs = offsets[: n + 1].cpu().numpy()
         data = scan[: int(offs[n])].cpu().numpy().tobytes()
         return [data[int(offs[i]): int(offs[i + 1])] for i in range(n)]

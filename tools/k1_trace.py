@@ -17,13 +17,17 @@ for _ in range(6):
 torch.cuda.synchronize()
 print("kernel times (events):", enc.kernel_times())
 strips = ((w + 255) // 256) * ((h + 7) // 8)
-nwarps = min((strips + 7) // 8, 296) * 8
+import ctypes
+grid, wpc = ctypes.c_int(0), ctypes.c_int(0)
+check(enc.lib.jpegb200_encoder_launch_shape(enc.handle, ctypes.byref(grid), ctypes.byref(wpc)), "launch_shape")
+nwarps = grid.value * wpc.value
+print("block kernel grid", grid.value, "x", wpc.value, "warps")
 tr = np.zeros((2 * nwarps, 8), np.uint64)
 check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, 2 * nwarps), "trace")
 t = tr[:nwarps].astype(np.int64)
 ends = tr[nwarps:].astype(np.int64)
 t0 = t[:, 0].min()
-names = ["entry", "prologue", "tile0", "pre-table", "table", "strip0-late", "exit"]
+names = ["entry", "prologue", "tile0", "-", "-", "-", "exit"]
 print("warps", nwarps, "strips", strips, "span us", (t[:, 6].max() - t0) / 1e3)
 for i, n in enumerate(names):
     col = t[:, i]
