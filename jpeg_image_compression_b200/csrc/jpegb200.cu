@@ -200,6 +200,8 @@ struct jpegb200_encoder {
     int bytes_per_block = 24;
     jb::HostTables tables;
     jb::DeviceBuffer coef, blkinfo, streams, strips, strip_bits, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace, trace1;
+    uint64_t *pinned_status = nullptr;   // host-pinned {err, pad, offsets[2]}: one D2H + one sync per host call
+    uint64_t last_scan_bytes = 0;        // size of the previous host-call result: the speculative D2H length
     uint32_t slot_bytes = 768;      // strip stream slot: 32 blocks x bytes_per_block
     bool want_taps = false;         // K1 also stores the stage taps (coefficients, per-block bit offsets)
     bool taps_valid = false;        // ... and did so in the last launch
@@ -645,6 +647,7 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
     for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->streams, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
                             &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace, &enc->trace1})
         b->release();
+    if (enc->pinned_status) cudaFreeHost(enc->pinned_status);
     delete enc;
 }
 
@@ -926,6 +929,35 @@ extern "C" int jpegb200_synth_rgb_device(uint8_t *d_rgb, int width, int height, 
 // If the caller's buffers are pinned (cudaHostAlloc / cudaHostRegister) the copies run at
 // PCIe speed, otherwise the driver stages them.
 
+// Common tail of the host entries: ONE stream synchronisation in the usual case.  The error word and the scan size
+// (32 bytes at misc[0..32)) go to a pinned status block, and the scan bytes are copied speculatively in the same
+// breath -- as many as the previous call produced plus a margin; only if this image turned out larger is the
+// remainder fetched with a second copy.
+static int fetch_scan_to_host(jpegb200_encoder *enc, const uint8_t *d_scan, uint64_t d_capacity, uint8_t *host_scan, uint64_t host_capacity,
+                              uint64_t *host_scan_bytes, cudaStream_t st, void *cuda_stream)
+{
+    if (!enc->pinned_status) JB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&enc->pinned_status), 64, cudaHostAllocDefault));
+    uint64_t guess = enc->last_scan_bytes ? enc->last_scan_bytes + enc->last_scan_bytes / 8 + 4096 : d_capacity / 8;
+    guess = std::min(std::min(guess, d_capacity), host_capacity);
+    JB_CUDA(cudaMemcpyAsync(enc->pinned_status, enc->misc.ptr, 32, cudaMemcpyDeviceToHost, st));
+    if (guess) JB_CUDA(cudaMemcpyAsync(host_scan, d_scan, guess, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t err = (uint32_t)enc->pinned_status[0];
+    const uint64_t n = enc->pinned_status[3];
+    if (err) return jpegb200_encoder_status(enc, cuda_stream);
+    *host_scan_bytes = n;
+    if (n > host_capacity) {
+        g_last_error = "host scan buffer too small";
+        return JPEGB200_ERR_OUTPUT;
+    }
+    enc->last_scan_bytes = n;
+    if (n > guess) {
+        JB_CUDA(cudaMemcpyAsync(host_scan + guess, d_scan + guess, n - guess, cudaMemcpyDeviceToHost, st));
+        JB_CUDA(cudaStreamSynchronize(st));
+    }
+    return JPEGB200_OK;
+}
+
 extern "C" int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_rgb, int width, int height,
                                     uint8_t *host_scan, uint64_t host_capacity, uint64_t *host_scan_bytes,
                                     void *cuda_stream)
@@ -948,20 +980,7 @@ extern "C" int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_r
     JB_CUDA(cudaMemcpyAsync(d_rgb, host_rgb, nrgb, cudaMemcpyHostToDevice, st));
     if ((rc = prepare(enc, d_rgb, width, height, 1, 0, 0))) return rc;
     if ((rc = encode_launch(enc, d_scan, cap, d_off, st))) return rc;
-    uint64_t offs[2] = {0, 0};
-    uint32_t err = 0;
-    JB_CUDA(cudaMemcpyAsync(offs, d_off, 16, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaMemcpyAsync(&err, misc_err(enc), 4, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    if (err) return jpegb200_encoder_status(enc, cuda_stream);
-    *host_scan_bytes = offs[1];
-    if (offs[1] > host_capacity) {
-        g_last_error = "host scan buffer too small";
-        return JPEGB200_ERR_OUTPUT;
-    }
-    JB_CUDA(cudaMemcpyAsync(host_scan, d_scan, offs[1], cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    return JPEGB200_OK;
+    return fetch_scan_to_host(enc, d_scan, cap, host_scan, host_capacity, host_scan_bytes, st, cuda_stream);
 }
 
 // ---- C ABI: BMP file image in, complete JPEG file out ---------------
@@ -1011,19 +1030,15 @@ extern "C" int jpegb200_encode_bmp_to_jpeg_host(jpegb200_encoder *enc, const uin
     const uint8_t *top = bottom_up ? d_pix + (uint64_t)(h - 1) * pitch : d_pix;
     if ((rc = prepare(enc, top, w, h, 1, need, 0, bottom_up ? -(int64_t)pitch : (int64_t)pitch, /*bgr=*/true))) return rc;
     if ((rc = encode_launch(enc, d_scan, cap, misc_offsets(enc), st))) return rc;
-    uint64_t offs[2] = {0, 0};
-    uint32_t err = 0;
-    JB_CUDA(cudaMemcpyAsync(offs, misc_offsets(enc), 16, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaMemcpyAsync(&err, misc_err(enc), 4, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    if (err) return jpegb200_encoder_status(enc, cuda_stream);
-    *jpeg_bytes = 328 + offs[1] + 2;
-    if (*jpeg_bytes > jpeg_capacity) { g_last_error = "JPEG output buffer too small"; return JPEGB200_ERR_OUTPUT; }
+    if (jpeg_capacity < 330) { g_last_error = "JPEG output buffer too small"; return JPEGB200_ERR_OUTPUT; }
+    uint64_t scan_bytes = 0;
+    rc = fetch_scan_to_host(enc, d_scan, cap, jpeg_out + 328, jpeg_capacity - 330, &scan_bytes, st, cuda_stream);
+    *jpeg_bytes = 328 + scan_bytes + 2;
+    if (rc == JPEGB200_ERR_OUTPUT) g_last_error = "JPEG output buffer too small";
+    if (rc) return rc;
     jpegb200_jfif_header(w, h, jpeg_out);
-    JB_CUDA(cudaMemcpyAsync(jpeg_out + 328, d_scan, offs[1], cudaMemcpyDeviceToHost, st));
-    JB_CUDA(cudaStreamSynchronize(st));
-    jpeg_out[328 + offs[1]] = 0xFF;                                  // EOI, jpeg_handler.c:113-117
-    jpeg_out[328 + offs[1] + 1] = 0xD9;
+    jpeg_out[328 + scan_bytes] = 0xFF;                               // EOI, jpeg_handler.c:113-117
+    jpeg_out[328 + scan_bytes + 1] = 0xD9;
     return JPEGB200_OK;
 }
 
