@@ -360,10 +360,9 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     }
     if (threadIdx.x < 64) s_cos[threadIdx.x] = c_ref_cos[threadIdx.x];
     mbar_fence_init();
-    if (TC && warp == 0) tmem_alloc(&s_tmem, Cfg::TMEM_COLS);
-    if (TC) tc_fence_before_sync();
-    __syncthreads();
-    if (TC) tc_fence_after_sync();
+    __syncwarp();
+    // The first strip's pixels are requested before the block-wide set-up below (TMEM allocation, barrier): a warp only
+    // needs its own mbarrier, which its lane 0 has just initialised and fenced.
     uint32_t phase = 0;
     StripCtx cur;
     StripPos pos;
@@ -371,12 +370,16 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     if (s < total) {
         pos = strip_pos(g, s);
         cur = strip_ctx(g, pos);
-        strip_issue_loads(cur, raw, bar, lane, tmap);                  // first strip's pixels are in flight ...
+        strip_issue_loads(cur, raw, bar, lane, tmap);
     }
-    if (TC && threadIdx.x == 0) {                                // ... while the limb matrix is staged (one 16 KB TMA bulk copy)
+    if (TC && threadIdx.x == 0) {                                // ... and the limb matrix (one 16 KB TMA bulk copy)
         mbar_expect_tx(table_bar, K1_BMAT_BYTES);
         bulk_g2s(smem, tables + TBL_BMAT, K1_BMAT_BYTES, table_bar);
     }
+    if (TC && warp == 0) tmem_alloc(&s_tmem, Cfg::TMEM_COLS);
+    if (TC) tc_fence_before_sync();
+    __syncthreads();
+    if (TC) tc_fence_after_sync();
     // reset the look-back state of the merge kernel (K2) that follows in the stream: keeps a
     // whole encode CUDA-graph replayable without a memset node
     for (uint64_t i = (uint64_t)blockIdx.x * Cfg::THREADS + threadIdx.x; i < lookback_words;

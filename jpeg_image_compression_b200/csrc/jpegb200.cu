@@ -483,7 +483,8 @@ static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool tap
     sa.blocks_per_image = g.blocks_per_image;
     enc->taps_valid = taps;
     const bool big = enc->slot_bytes > (uint32_t)STREAM_SMALL_BYTES;
-    const uint64_t want = (g.total_strips + 7) / 8;
+    const uint64_t warps = big ? K1bCfg<true>::WARPS : K1bCfg<false>::WARPS;
+    const uint64_t want = (g.total_strips + warps - 1) / warps;
     const int per_sm = big ? K1bCfg<true>::CTAS_PER_SM : K1bCfg<false>::CTAS_PER_SM;
     int grid = (int)std::min<uint64_t>(want, (uint64_t)enc->sm_count * per_sm);
     if (const char *e = getenv("JPEGB200_K1B_GRID")) grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, atoi(e)));   // tuning aid

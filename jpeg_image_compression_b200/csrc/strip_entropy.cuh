@@ -28,9 +28,9 @@ constexpr int K1B_SYM_BYTES = 16384;                 // AC symbol table staged i
 
 template <bool BIGWIN>
 struct K1bCfg {
-    static constexpr int WARPS = 8;
+    static constexpr int WARPS = BIGWIN ? 8 : 16;                    // the 16 KB symbol table is shared by the CTA's warps
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int CTAS_PER_SM = BIGWIN ? 1 : 3;
+    static constexpr int CTAS_PER_SM = BIGWIN ? 1 : 2;               // 32 warps per SM at <= 64 registers
     static constexpr int STREAM_BYTES = BIGWIN ? STREAM_BIG_BYTES : STREAM_SMALL_BYTES;
     static constexpr int WIN_BYTES = STREAM_BYTES + 128;             // + slack: the bit writer may touch one word past the end
     static constexpr int ZS_PITCH = 17;                              // words per lane of the coefficient staging area (conflict-free byte reads)

@@ -226,13 +226,19 @@ def test_batch_1080p_hashes(enc, synth_hashes):
 
 
 def test_workspace_overflow_is_reported_not_silent(oracle):
+    import torch
     e = jb.DeviceEncoder(0, bytes_per_block=2)
     rng = np.random.default_rng(1)
     rgb = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    # the device API never hides an overflow: the launch succeeds, the status call reports it
+    e.encode_device(torch.from_numpy(rgb).cuda(), 64, 64, 1)
     with pytest.raises(jb.JpegB200Error):
-        e.encode(rgb)
+        e.status()
+    # the convenience entries (Python encode / encode_batch, C jpegb200_encode_scan, the batch CLI) retry with the
+    # worst-case workspace and still match
+    assert e.encode(rgb) == oracle.encode_scan(rgb)
+    assert e.bytes_per_block == 184
     e.close()
-    # the host entry retries with the worst-case workspace and still matches
     assert jb.encode_scan_host(rgb) == oracle.encode_scan(rgb)
 
 
