@@ -560,9 +560,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         sync_all()
         enc.status()
         bms = max_over_ranks(e0.elapsed_time(e1)) / nb_steps
+        verified = None
+        key = "1920x1080_seed64_amp20"                       # image 63 of the batch (seed 1 + 63): rank 0 owns it
+        if rank == 0 and key in hashes and chunks and chunks[0][0] == 0 and chunks[0][1] > 63:
+            enc.encode_device(cins[0], bw_, bh_, chunks[0][1] - chunks[0][0], scan=cscan, offsets=coffs)
+            enc.status()
+            o63, o64 = int(coffs[63].item()), int(coffs[64].item())
+            ok = (o64 - o63) == hashes[key]["scan_bytes"] and \
+                hashlib.sha256(cscan[o63:o64].cpu().numpy().tobytes()).hexdigest() == hashes[key]["scan_sha256"]
+            verified = "image 63 byte-identical to the reference build (sha256)" if ok else "MISMATCH"
         extra["batch1080p_4096"] = {"config": "BASELINE configs[3]", "scaling": "strong", "images_total": total_images,
                                     "images_this_rank": hi - lo, "ms_per_batch": round(bms, 4), "steps": nb_steps,
-                                    "value": round(total_images * bw_ * bh_ / (bms * 1e-3) / 1e6, 1), "unit": UNIT}
+                                    "value": round(total_images * bw_ * bh_ / (bms * 1e-3) / 1e6, 1), "unit": UNIT,
+                                    "verified": verified}
         del cins, cscan, coffs
         torch.cuda.empty_cache()
 
@@ -701,7 +711,7 @@ def main():
     ap.add_argument("--workload", default="uhd4k", choices=["uhd4k", "batch1080p"])
     ap.add_argument("--batch", type=int, default=512, help="images per step per GPU for batch1080p")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="encoder handles / streams with independent images in flight")
+    ap.add_argument("--streams", type=int, default=8, help="encoder handles / streams with independent images in flight")
     ap.add_argument("--no-extras", action="store_true", help="skip config.extra (the sharded BASELINE configs)")
     ap.add_argument("--no-giga", action="store_true", help="skip the 32768x32768 stripe row of config.extra")
     ap.add_argument("--extra-images", type=int, default=4096, help="total images of the strong-scaling batch row")

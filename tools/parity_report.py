@@ -33,6 +33,11 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         cases = [(os.path.basename(f), f) for f in args.files]
         if not cases:
+            # BASELINE configs[0]: the reference's own assets at full size (copied next to oracle/_ref by build())
+            adir = os.path.join(ROOT, "oracle", "_ref", "assets")
+            for n in ("lena", "blackbuck", "greenland", "offset_sample"):
+                if os.path.exists(os.path.join(adir, n + ".bmp")):
+                    cases.append(("asset_" + n, os.path.join(adir, n + ".bmp")))
             for name, (w, h, seed, amp) in {"synth_1920x1080_amp20": (1920, 1080, 0, 20), "synth_3840x2160_amp20": (3840, 2160, 1, 20),
                                             "synth_3840x2160_amp0": (3840, 2160, 1, 0), "synth_3840x2160_amp64": (3840, 2160, 1, 64),
                                             "synth_762x1309_amp20": (762, 1309, 5, 20), "synth_1283x725_amp20": (1283, 725, 9, 20)}.items():
