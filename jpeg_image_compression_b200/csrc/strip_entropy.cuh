@@ -114,48 +114,77 @@ struct SymWalk {
 __device__ __forceinline__ SymWalk cache_symbols(uint32_t zs, uint32_t mlo, uint32_t mhi, uint32_t sym, uint32_t cptr, uint32_t climit)
 {
     SymWalk w;
-    w.bits = 0;
-    w.rest_lo = w.rest_hi = 0;
-    w.rest_prev = -1;
-    const uint32_t zrl_len = lds_u32(sym + 4u * 0x80u) & 31u, eob = lds_u32(sym);
-    int prev = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t m = half ? mhi : mlo;
+    const uint32_t eob = lds_u32(sym);
+    uint32_t bits = 0;
+    uint32_t rest_lo = 0, rest_hi = 0;
+    int rest_prev = -1, prev = 0;
+    // fast loops: one per half of the map; they leave through `spill` at the first coefficient that is not cached
+    {
+        uint32_t m = mlo;
 #pragma unroll 1
         while (m) {
-            const int k = 32 * half + __ffs((int)m) - 1;
+            const int k = __ffs((int)m) - 1;
             const uint32_t byte = lds_u8(zs + (uint32_t)k);
             const uint32_t run = (uint32_t)(k - prev - 1);
-            const uint32_t e = lds_u32(sym + ((((run & 15u) << 8) | byte) << 2));
-            w.bits += (run >> 4) * zrl_len + (e & 31u);                                // ZRLs: rle.c:99-103
-            if (w.rest_prev < 0) {                                                     // still caching
-                if (run < 16u && cptr < climit) {
-                    sts_u32(cptr, e);
-                    cptr += 128u;
-                } else {                                                               // the rest goes the long way
-                    w.rest_lo = half ? 0u : m;
-                    w.rest_hi = half ? m : mhi;
-                    w.rest_prev = prev;
-                }
-            }
+            if (run >= 16u || cptr == climit) { rest_lo = m; rest_hi = mhi; rest_prev = prev; goto spill; }
+            const uint32_t e = lds_u32(sym + (((run << 8) | byte) << 2));
+            bits += e & 31u;
+            sts_u32(cptr, e);
+            cptr += 128u;
+            m &= m - 1;
+            prev = k;
+        }
+        m = mhi;
+#pragma unroll 1
+        while (m) {
+            const int k = 32 + __ffs((int)m) - 1;
+            const uint32_t byte = lds_u8(zs + (uint32_t)k);
+            const uint32_t run = (uint32_t)(k - prev - 1);
+            if (run >= 16u || cptr == climit) { rest_hi = m; rest_prev = prev; goto spill; }
+            const uint32_t e = lds_u32(sym + (((run << 8) | byte) << 2));
+            bits += e & 31u;
+            sts_u32(cptr, e);
+            cptr += 128u;
             m &= m - 1;
             prev = k;
         }
     }
-    w.last = prev;
     if (prev < 63) {                                                                   // EOB, rle.c:121-123
-        w.bits += eob & 31u;
-        if (w.rest_prev < 0) {
-            if (cptr < climit) {
-                sts_u32(cptr, eob);
-                cptr += 128u;
-            } else {
-                w.rest_prev = prev;                                                    // only the EOB is left for emit_tail
-            }
+        bits += eob & 31u;
+        if (cptr != climit) {
+            sts_u32(cptr, eob);
+            cptr += 128u;
+        } else {
+            rest_prev = prev;                                                          // only the EOB is left for emit_tail
         }
     }
+    w.last = prev;
+    goto done;
+spill:
+    {   // rare: cost of the coefficients that are not cached (emit_tail walks them again)
+        const uint32_t zrl_len = lds_u32(sym + 4u * 0x80u) & 31u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t m = half ? rest_hi : rest_lo;
+#pragma unroll 1
+            while (m) {
+                const int k = 32 * half + __ffs((int)m) - 1;
+                m &= m - 1;
+                const uint32_t byte = lds_u8(zs + (uint32_t)k);
+                const uint32_t run = (uint32_t)(k - prev - 1);
+                prev = k;
+                bits += (run >> 4) * zrl_len + (lds_u32(sym + ((((run & 15u) << 8) | byte) << 2)) & 31u);   // ZRLs: rle.c:99-103
+            }
+        }
+        if (prev < 63) bits += eob & 31u;
+        w.last = prev;
+    }
+done:
+    w.bits = bits;
     w.cend = cptr;
+    w.rest_lo = rest_lo;
+    w.rest_hi = rest_hi;
+    w.rest_prev = rest_prev;
     return w;
 }
 
