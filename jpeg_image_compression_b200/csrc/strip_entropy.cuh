@@ -268,23 +268,41 @@ k_strip_entropy(const StripArgs a)
     const uint32_t cap_bits = a.slot_bytes * 8u;
     bool table_ready = false;
 
-    // strip -> (first block, blocks, first-of-image)
-    auto locate = [&](uint32_t s, uint64_t &block0, uint32_t &vb, bool &first) {
-        const uint32_t img = s / per_image, rem = s - img * per_image;
-        const uint32_t brow = rem / a.spr, sx = rem - brow * a.spr;
-        block0 = (uint64_t)img * a.blocks_per_image + (uint64_t)brow * a.bw + sx * 32u;
-        vb = min(32u, a.bw - sx * 32u);
-        first = rem == 0;
+    // strip -> (first block, blocks, first-of-image).  The position is found by division once and then advanced
+    // incrementally (a warp's strips are `stride` apart).
+    uint32_t s = blockIdx.x * Cfg::WARPS + warp;
+    uint32_t p_img = s / per_image, p_brow, p_sx;
+    {
+        const uint32_t rem = s - p_img * per_image;
+        p_brow = rem / a.spr;
+        p_sx = rem - p_brow * a.spr;
+    }
+    const uint32_t dq = stride / a.spr, dr = stride - dq * a.spr;
+    auto locate = [&](uint64_t &block0, uint32_t &vb, bool &first) {
+        block0 = (uint64_t)p_img * a.blocks_per_image + (uint64_t)p_brow * a.bw + p_sx * 32u;
+        vb = min(32u, a.bw - p_sx * 32u);
+        first = (p_brow | p_sx) == 0u;
+    };
+    auto advance = [&]() {
+        p_sx += dr;
+        p_brow += dq;
+        if (p_sx >= a.spr) {
+            p_sx -= a.spr;
+            ++p_brow;
+        }
+        while (p_brow >= a.bh) {
+            p_brow -= a.bh;
+            ++p_img;
+        }
     };
 
-    uint32_t s = blockIdx.x * Cfg::WARPS + warp;
     uint64_t block0 = 0;
     uint32_t vb = 0;
     bool first = false;
     uint4 q[4];
     int pred = 0;                                                // lane 0: quantized DC of the block before the strip
     if (s < a.total_strips) {
-        locate(s, block0, vb, first);
+        locate(block0, vb, first);
         if ((uint32_t)lane < vb) {
             const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 64);
 #pragma unroll
@@ -313,7 +331,8 @@ k_strip_entropy(const StripArgs a)
         }
         // request the next strip's coefficients now: their latency hides behind the walks below
         if (s + stride < a.total_strips) {
-            locate(s + stride, block0, vb, first);
+            advance();
+            locate(block0, vb, first);
             if ((uint32_t)lane < vb) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 64);
 #pragma unroll
@@ -386,8 +405,9 @@ k_strip_entropy(const StripArgs a)
                 a.strip_bits[s] = strip_total;
                 if (!fits) atomicOr(a.err, ERRBIT_WORKSPACE);
             }
-            if (a.dbg_blkinfo && (uint32_t)lane < my_vb)          // stage tap for the parity tests
-                a.dbg_blkinfo[my_block0 + (uint32_t)lane] = (incl - my_bits) | ((uint32_t)sw.last << 16);
+            if (a.dbg_blkinfo != nullptr) {                      // stage tap for the parity tests (uniform branch)
+                if ((uint32_t)lane < my_vb) a.dbg_blkinfo[my_block0 + (uint32_t)lane] = (incl - my_bits) | ((uint32_t)sw.last << 16);
+            }
         }
         __syncwarp();
     }

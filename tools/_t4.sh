@@ -1,6 +1,6 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
 B="python bench.py --no-cpu-baseline --no-sensitivity"
-run() { name=$1; shift; "$@" > gpurun_out/r2o_$name.json 2> gpurun_out/r2o_$name.err; python - gpurun_out/r2o_$name.json $name <<'PY'
+run() { name=$1; shift; "$@" > gpurun_out/r2p_$name.json 2> gpurun_out/r2p_$name.err; python - gpurun_out/r2p_$name.json $name <<'PY'
 import json,sys
 for l in open(sys.argv[1]):
     l=l.strip()
