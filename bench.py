@@ -40,12 +40,18 @@ if ROOT not in sys.path:
 # stdout must carry exactly ONE JSON line, but native libraries (e.g. NCCL's version banner) write to
 # file descriptor 1 too: park the real stdout, point fd 1 at stderr for the whole run, and emit the
 # result line on the parked descriptor at the end.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def park_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line: dict) -> None:
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 METRIC = "Mpixel/s BMP->JPEG encode (natural_c hot path)"
@@ -703,6 +709,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
 
 def main():
+    park_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 20000 for uhd4k, 200 for batch1080p, 100 for --impl reference)")

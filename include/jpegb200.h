@@ -251,7 +251,9 @@ int jpegb200_encoder_launch_shape(jpegb200_encoder *enc, int *k1_grid, int *k1_w
  * last stripe, which carries the ragged bottom); halo_rows = pixel rows of the NEXT stripe's
  * first block row that follow in the same buffer (min(8, rows left); 0 for the last stripe).
  * The halo lets a rank finish the byte its stream ends in without receiving bits from its
- * neighbour.  Two phases with one tiny exchange between them (done by the caller over NCCL;
+ * neighbour.  As for jpegb200_batch, pixel rows are fetched in whole 16-byte lines: up to 15 bytes before the
+ * first and after the last pixel byte of the stripe buffer may be read (never used) and must be readable device
+ * memory (true for any pointer into a cudaMalloc'd or pooled allocation).  Two phases with one tiny exchange between them (done by the caller over NCCL;
  * see INTEGRATION.md and jpeg_image_compression_b200/stripes.py):
  *
  *   analyze : fused block kernel over the stripe (+ halo) -> {first_dc, last_dc, bits_pred0}
