@@ -214,6 +214,7 @@ struct jpegb200_encoder {
     int k2_ctas_per_sm[2] = {0, 0};
     int k1_grid = 0, k1_warps = 0;   // shape of the last K1 launch
     bool stripe_ready = false;
+    bool stripe_state_fresh = false;   // K2's look-back state is still the zeroed one K1 left (no memset before the first stripe encode)
     // optional per-kernel timing (cudaEvents on the launching stream)
     bool profiling = false;
     std::vector<cudaEvent_t> events;        // 2 per timed kernel of the last launch
@@ -351,7 +352,8 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     a.count = count;
     a.dc_pred0 = 0;
     a.bit_phase = 0;
-    a.dyn = nullptr;
+    a.dyn_all = nullptr;
+    a.dyn_rank = 0;
     a.trace = nullptr;
     if (getenv("JPEGB200_K2_TRACE")) {              // tuning aid: per-tile phase timestamps
         if ((rc = enc->trace.reserve((uint64_t)tiles * count * 64))) return rc;
@@ -464,7 +466,7 @@ static int launch_block_kernel(jpegb200_encoder *enc, cudaStream_t st, bool stat
 }
 
 // K1b: strip entropy kernel (persistent) -> strip bit streams + strip records
-static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool taps)
+static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool taps, void *d_summary = nullptr)
 {
     const Geom &g = enc->geom;
     StripArgs sa;
@@ -481,6 +483,10 @@ static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool tap
     sa.bw = (uint32_t)g.bw;
     sa.bh = (uint32_t)g.bh;
     sa.blocks_per_image = g.blocks_per_image;
+    sa.summary = d_summary;                         // stripes: reduced by the CTA that finishes last
+    sa.summary_strips = enc->args.strips_owned;
+    // a spare word of the line that holds K2's tile ticket: K1's prologue has zeroed it
+    sa.done_counter = reinterpret_cast<unsigned int *>(static_cast<uint64_t *>(enc->lookback.ptr) + (enc->lookback_words - 8));
     enc->taps_valid = taps;
     const bool big = enc->slot_bytes > (uint32_t)STREAM_SMALL_BYTES;
     const uint64_t warps = big ? K1bCfg<true>::WARPS : K1bCfg<false>::WARPS;
@@ -825,9 +831,8 @@ extern "C" int jpegb200_encoder_read_block_bits(jpegb200_encoder *enc, uint32_t 
 // ---- C ABI: MCU-row stripes -------------------------------------------------------------
 
 // misc layout (256 bytes): [0] uint32 err, [8] uint64 flagged counter, [16] uint64[2] scan offsets,
-// [64] stripe summary (16 bytes), [96] StripeDyn (24 bytes)
+// [64] stripe summary (16 bytes)
 static StripeSummaryDev *misc_summary(jpegb200_encoder *e) { return reinterpret_cast<StripeSummaryDev *>(static_cast<uint8_t *>(e->misc.ptr) + 64); }
-static StripeDyn *misc_dyn(jpegb200_encoder *e) { return reinterpret_cast<StripeDyn *>(static_cast<uint8_t *>(e->misc.ptr) + 96); }
 
 extern "C" int jpegb200_stripe_analyze_device(jpegb200_encoder *enc, const uint8_t *d_rgb, int width, int stripe_height,
                                               int halo_rows, jpegb200_stripe_summary *d_out, void *cuda_stream)
@@ -838,12 +843,9 @@ extern "C" int jpegb200_stripe_analyze_device(jpegb200_encoder *enc, const uint8
     if (rc) return rc;
     enc->launches = 0;
     if ((rc = launch_block_kernel(enc, st))) return rc;
-    if ((rc = launch_strip_entropy(enc, st, enc->want_taps))) return rc;
-    const PackArgs &a = enc->args;
-    ++enc->launches;
-    k_stripe_summary<<<1, 256, 0, st>>>(a.strips, a.strip_bits, a.strips_owned, reinterpret_cast<StripeSummaryDev *>(d_out));
-    JB_CUDA(cudaGetLastError());
+    if ((rc = launch_strip_entropy(enc, st, enc->want_taps, d_out))) return rc;
     enc->stripe_ready = true;
+    enc->stripe_state_fresh = true;                 // K1's prologue has just cleared K2's look-back state
     return JPEGB200_OK;
 }
 
@@ -860,17 +862,21 @@ extern "C" int jpegb200_stripe_analyze(jpegb200_encoder *enc, const uint8_t *d_r
     return JPEGB200_OK;
 }
 
-// K2 for a stripe; dyn == nullptr: predictor and phase come from enc->args (host values)
-static int stripe_encode_launch(jpegb200_encoder *enc, const StripeDyn *dyn, uint8_t *d_scan, uint64_t scan_capacity, uint64_t *d_scan_info,
-                                cudaStream_t st)
+// K2 for a stripe; d_all == nullptr: predictor and phase come from enc->args (host values), otherwise the kernel derives
+// them from all ranks' summaries in device memory
+static int stripe_encode_launch(jpegb200_encoder *enc, const StripeSummaryDev *d_all, int rank, uint8_t *d_scan, uint64_t scan_capacity,
+                                uint64_t *d_scan_info, cudaStream_t st)
 {
     PackArgs &a = enc->args;
-    a.dyn = dyn;
+    a.dyn_all = d_all;
+    a.dyn_rank = rank;
     a.out = d_scan;
     a.out_capacity = scan_capacity;
     a.out_slot = 0;
     a.scan_offsets = d_scan_info;
-    JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));   // idempotent re-runs
+    if (!enc->stripe_state_fresh)                   // a second encode after one analyze: clear K2's look-back state again
+        JB_CUDA(cudaMemsetAsync(enc->lookback.ptr, 0, enc->lookback_words * 8, st));
+    enc->stripe_state_fresh = false;
     return launch_entropy(enc, st);
 }
 
@@ -883,10 +889,7 @@ extern "C" int jpegb200_stripe_encode_device(jpegb200_encoder *enc, const jpegb2
     }
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     JB_CUDA(cudaSetDevice(enc->device));
-    ++enc->launches;
-    k_stripe_resolve<<<1, 32, 0, st>>>(reinterpret_cast<const StripeSummaryDev *>(d_all), rank, misc_dyn(enc));
-    JB_CUDA(cudaGetLastError());
-    return stripe_encode_launch(enc, misc_dyn(enc), d_scan, scan_capacity, d_scan_info, st);
+    return stripe_encode_launch(enc, reinterpret_cast<const StripeSummaryDev *>(d_all), rank, d_scan, scan_capacity, d_scan_info, st);
 }
 
 extern "C" int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predictor, uint64_t bit_begin, uint8_t *d_scan,
@@ -900,7 +903,7 @@ extern "C" int jpegb200_stripe_encode(jpegb200_encoder *enc, int16_t dc_predicto
     JB_CUDA(cudaSetDevice(enc->device));
     enc->args.dc_pred0 = dc_predictor;
     enc->args.bit_phase = (uint32_t)(bit_begin & 7u);
-    int rc = stripe_encode_launch(enc, nullptr, d_scan, scan_capacity, misc_offsets(enc), st);
+    int rc = stripe_encode_launch(enc, nullptr, 0, d_scan, scan_capacity, misc_offsets(enc), st);
     if (rc) return rc;
     uint64_t offs[2] = {0, 0};
     JB_CUDA(cudaMemcpyAsync(offs, misc_offsets(enc), 16, cudaMemcpyDeviceToHost, st));

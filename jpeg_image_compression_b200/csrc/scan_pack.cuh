@@ -39,13 +39,13 @@ constexpr int K2_STAGE_BYTES = 2 * 4 * K2_ROUND_WORDS + 32;    // stuffed bytes 
 __host__ __device__ constexpr int k2_win_words(int slot_bytes) { return K2_TILE_STRIPS * slot_bytes / 4 + 8; }
 __host__ __device__ constexpr int k2_smem(int slot_bytes) { return 2 * k2_win_words(slot_bytes) * 4 + K2_STAGE_BYTES; }
 
-// stripes: values that are only known after the ranks' exchange may be read from device memory (written by
-// k_stripe_resolve), so that analyze -> exchange -> encode needs no host round trip
-struct StripeDyn {
-    int32_t dc_pred0;              // DC predictor of the stripe's first block
-    uint32_t bit_phase;            // global bit offset of the stripe & 7
-    uint64_t bit_begin;            // global bit offset of the stripe
-    uint64_t byte_begin;           // first stream byte the stripe owns (unstuffed)
+// stripes: boundary summary of one stripe (= jpegb200_stripe_summary).  bits_pred0 = the stripe's bit count if its
+// first block were predicted from DC 0 (the strips' counts lack exactly that one symbol).
+struct StripeSummaryDev {
+    int16_t first_dc;
+    int16_t last_dc;
+    uint32_t valid;              // 1: the rank owns block rows; 0: empty slot
+    uint64_t bits_pred0;
 };
 
 struct PackArgs {
@@ -70,7 +70,8 @@ struct PackArgs {
     int count;
     int16_t dc_pred0;              // DC predictor of the image's first block (0; stripes: previous stripe's last DC)
     uint32_t bit_phase;            // bit offset of the first bit inside byte 0 (0; stripes: global phase & 7)
-    const StripeDyn *dyn;          // if set: dc_pred0 / bit_phase are read from device memory instead
+    const StripeSummaryDev *dyn_all;   // stripes, device-resident exchange: all ranks' summaries (device memory); if set,
+    int dyn_rank;                      // dc_pred0 / bit_phase are derived from them in the kernel's prologue
     unsigned long long *trace;     // optional [tiles*count][8] phase timestamps (ns), tuning aid; nullptr in production
 };
 
@@ -176,8 +177,22 @@ k_merge_stuff(const PackArgs a, const int win_words)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_next_tile = atomicAdd(a.tile_counter, 1ull);
     for (int i = tid; i < win_words / 2; i += K2_THREADS) reinterpret_cast<uint4 *>(k2_smem_words)[i] = make_uint4(0u, 0u, 0u, 0u);   // both windows
-    const int32_t dc_pred0 = a.dyn ? a.dyn->dc_pred0 : (int32_t)a.dc_pred0;
-    const uint32_t bit_phase = a.dyn ? a.dyn->bit_phase : a.bit_phase;
+    int32_t dc_pred0 = (int32_t)a.dc_pred0;
+    uint32_t bit_phase = a.bit_phase;
+    if (a.dyn_all != nullptr) {
+        // stripes: this rank's DC predictor and global bit offset from all ranks' summaries (the device version of
+        // stripes.resolve_offsets: the true cost of a stripe's first DC symbol replaces the predictor-0 cost)
+        uint64_t bit = 0;
+        int pred = 0;
+        for (int r = 0; r < a.dyn_rank; ++r) {
+            const StripeSummaryDev sr = a.dyn_all[r];
+            if (!sr.valid) continue;
+            bit += sr.bits_pred0 - c_dc_len[magnitude_class_k2((int)sr.first_dc)] + c_dc_len[magnitude_class_k2((int)sr.first_dc - pred)];
+            pred = sr.last_dc;
+        }
+        dc_pred0 = pred;
+        bit_phase = (uint32_t)(bit & 7u);
+    }
     const uint64_t origin = ((uint64_t)bit_phase + 7) >> 3;       // first stream byte this image/stripe owns
     const int groups = (a.tiles + LB_GROUP - 1) / LB_GROUP;
     const uint64_t total_tiles = (uint64_t)a.tiles * (uint64_t)a.count;
@@ -442,57 +457,6 @@ k_merge_stuff(const PackArgs a, const int win_words)
 }
 
 // ---------------------------------------------------------------------------------
-// stripes: boundary summary of one stripe, reduced on the device (one CTA).  bits_pred0 = the stripe's bit count if
-// its first block were predicted from DC 0 (the strips' counts lack exactly that one symbol).
-struct StripeSummaryDev {        // = jpegb200_stripe_summary
-    int16_t first_dc;
-    int16_t last_dc;
-    uint32_t valid;              // 1: the rank owns block rows; 0: empty slot
-    uint64_t bits_pred0;
-};
-
-__global__ void __launch_bounds__(256)
-k_stripe_summary(const StripRec *__restrict__ strips, const uint32_t *__restrict__ strip_bits, const uint32_t strips_owned,
-                 StripeSummaryDev *__restrict__ out)
-{
-    __shared__ uint64_t s_part[8];
-    uint64_t sum = 0;
-    for (uint32_t i = threadIdx.x; i < strips_owned; i += 256) sum += strip_bits[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t bits = 0;
-        for (int w = 0; w < 8; ++w) bits += s_part[w];
-        const int first_dc = strips[0].first_dc;
-        bits += c_dc_len[magnitude_class_k2(first_dc)];           // first DC symbol, predictor 0 (rle.c:68-76)
-        out->first_dc = (int16_t)first_dc;
-        out->last_dc = strips[strips_owned - 1].last_dc;
-        out->valid = 1u;
-        out->bits_pred0 = bits;
-    }
-}
-
-// stripes: from all ranks' summaries derive this rank's DC predictor and global bit offset (the device version of
-// stripes.resolve_offsets): the true cost of a stripe's first DC symbol replaces the predictor-0 cost.
-__global__ void k_stripe_resolve(const StripeSummaryDev *__restrict__ all, const int rank, StripeDyn *__restrict__ dyn)
-{
-    if (threadIdx.x != 0) return;
-    uint64_t bit = 0;
-    int pred = 0;
-    for (int r = 0; r < rank; ++r) {
-        if (!all[r].valid) continue;
-        const int fd = all[r].first_dc;
-        bit += all[r].bits_pred0 - c_dc_len[magnitude_class_k2(fd)] + c_dc_len[magnitude_class_k2(fd - pred)];
-        pred = all[r].last_dc;
-    }
-    dyn->dc_pred0 = pred;
-    dyn->bit_phase = (uint32_t)(bit & 7u);
-    dyn->bit_begin = bit;
-    dyn->byte_begin = (bit + 7) >> 3;
-}
-
 // ---------------------------------------------------------------------------------
 // batch mode: exclusive scan of the stuffed image sizes -> scan_offsets[count+1]  (one CTA)
 // `extra`: bytes that frame every image in the output besides its scan (0, or 330 in files mode: the

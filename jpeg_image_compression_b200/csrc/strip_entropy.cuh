@@ -233,6 +233,11 @@ struct StripArgs {
     uint32_t total_strips;
     uint32_t spr, bw, bh;          // strips per block row, blocks per block row, block rows per image
     uint64_t blocks_per_image;
+    // stripes: the CTA that finishes last reduces the stripe's boundary summary {first DC, last DC, bits if the first
+    // block were predicted from 0} over the `summary_strips` owned strips into *summary (device memory, 16 bytes)
+    void *summary;                 // nullptr: no summary
+    uint32_t summary_strips;
+    unsigned int *done_counter;    // zeroed before the launch (part of the look-back state K1 clears)
 };
 
 template <bool BIGWIN>
@@ -410,6 +415,39 @@ k_strip_entropy(const StripArgs a)
             }
         }
         __syncwarp();
+    }
+
+    if (a.summary != nullptr) {
+        // last-CTA-done reduction (stripes): every CTA publishes its strip records, the one that arrives last sums them
+        __shared__ bool s_last;
+        __shared__ uint64_t s_part[Cfg::WARPS];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(a.done_counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            uint64_t sum = 0;
+            for (uint32_t i = threadIdx.x; i < a.summary_strips; i += Cfg::THREADS) sum += __ldcg(a.strip_bits + i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) s_part[warp] = sum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint64_t bits = 0;
+                for (int w = 0; w < Cfg::WARPS; ++w) bits += s_part[w];
+                const volatile StripRec *recs = a.strips;           // written by other CTAs of this launch
+                const int first_dc = recs[0].first_dc;
+                const uint32_t dc_entry = s_dc[magnitude_class(first_dc)];
+                bits += (dc_entry & 0xFFu) + (uint32_t)magnitude_class(first_dc);       // first DC symbol, predictor 0 (rle.c:68-76)
+                struct { int16_t first_dc, last_dc; uint32_t valid; uint64_t bits_pred0; } out;
+                out.first_dc = (int16_t)first_dc;
+                out.last_dc = recs[a.summary_strips - 1].last_dc;
+                out.valid = 1u;
+                out.bits_pred0 = bits;
+                *reinterpret_cast<decltype(out) *>(a.summary) = out;
+            }
+        }
     }
 }
 
