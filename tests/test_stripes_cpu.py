@@ -85,8 +85,11 @@ def _rank_main(rank, world, port, w, h, seed, result_path):
         scan = np.zeros(4 * w * max(owned, 1) + 64, np.uint8)
         n = enc.encode(rgb[y0:y0 + owned + halo], w, h, scan)
         stitched = enc.gather(scan, n)
+        # the size-exact gather (sizes all-gathered as tensors, then send / recv of exactly each rank's bytes)
+        import torch
+        exact, total = enc.gather_exact(torch.from_numpy(scan), torch.tensor(n, dtype=torch.int64))
         if rank == 0:
-            ok = stitched == oracle.encode_scan(rgb)
+            ok = stitched == oracle.encode_scan(rgb) and exact[:total].numpy().tobytes() == stitched
             with open(result_path, "w") as f:
                 f.write("ok" if ok else f"mismatch: {len(stitched)} bytes")
     finally:
