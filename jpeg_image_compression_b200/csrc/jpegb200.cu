@@ -503,7 +503,7 @@ static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool tap
     return JPEGB200_OK;
 }
 
-// K2: scan + shift-merge + stuff over tiles of 8 strips; as many CTAs as can be co-resident (at most one per tile),
+// K2: scan + shift-merge + stuff over tiles of 16 strips; as many CTAs as can be co-resident (at most one per tile),
 // drawing tiles by ticket
 static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {

@@ -5,16 +5,15 @@
 // contiguous MSB-first bit stream (huffman.c:35-62) with a zero byte stuffed after every 0xFF (huffman.c:26-32)
 // and a zero-padded last byte (huffman.c:65-81).
 //
-// K1 leaves, per 32-block strip, its complete entropy-coded bits (left-aligned in a slot of its own; every
+// K1b leaves, per 32-block strip, its complete entropy-coded bits (left-aligned in a slot of its own; every
 // DC-difference symbol included, except the image's very first one) and a record {bits, first DC, last DC}, so
 // everything that crosses strips collapses to two prefix sums and a shift:
 //
-//   tile = 8 consecutive strips, one CTA
+//   tile = 16 consecutive strips, one CTA of 4 warps
 //   1. the bit counts of the earlier strips are requested up front; the tile's bit offset is their plain sum
 //      (wait-free; one checkpoint word per 1024 tiles);
-//   2. every thread assembles words of the tile's part of the image stream: it finds the strip(s) its word
-//      overlaps and funnel-shifts their stream words to the global bit phase (plain loads, plain stores, no
-//      atomics, no zero-initialised window);
+//   2. a warp takes every fourth strip of the tile: its lanes load the strip's stream words (coalesced), funnel-shift
+//      them to the global bit phase and OR-reduce them into the tile's pre-zeroed window in shared memory;
 //   3. bytes are owned by the tile that holds their first bit: the last, partial byte is completed with the
 //      leading bits of the following strip(s), the first partial byte is skipped -- no bits ever cross CTAs
 //      through global memory;

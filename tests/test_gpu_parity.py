@@ -157,7 +157,7 @@ def test_kernel_timing_taps(enc):
 
 
 def test_cuda_graph_replay_is_correct(enc, oracle):
-    """The two-kernel encode is graph-capturable: look-back state is reset by K1 itself."""
+    """The three-kernel encode is graph-capturable: the merge kernel's look-back state is reset by K1 itself."""
     import torch
     rgbs = [oracle.synth_rgb(512, 256, s, 25) for s in (1, 2)]
     d = [torch.from_numpy(r).cuda() for r in rgbs]
@@ -468,7 +468,7 @@ def test_extreme_aspect_ratios(enc, oracle):
 
 def test_many_tiles_cross_group_checkpoint(enc, oracle):
     """More than 1024 K2 tiles in one image exercises the look-back group checkpoints."""
-    w, h = 256, 8 * 8 * 1030 + 8                      # 1 strip per block row, 8 strips per tile -> 1031 tiles
+    w, h = 256, 8 * 16 * 1030 + 8                     # 1 strip per block row, 16 strips per tile (K2_TILE_STRIPS) -> 1031 tiles
     rgb = oracle.synth_rgb(w, h, 77, 30)
     assert enc.encode(rgb) == oracle.encode_scan(rgb)
 
@@ -543,6 +543,26 @@ def test_two_streams_many_tiles_no_deadlock(synth_hashes):
     for s, o in outs:
         n = int(o[1].item())
         assert n == e["scan_bytes"] and hashlib.sha256(s[:n].cpu().numpy().tobytes()).hexdigest() == e["scan_sha256"]
+    # a taller image: 2700 merge tiles per encode, more than the ~1000 CTAs that can be resident
+    w2, h2 = 7680, 11520
+    d2 = encs[0].synth(w2, h2, 1, 3, 20)
+    s0, o0 = encs[0].encode_device(d2, w2, h2, 1)
+    encs[0].status()
+    want = s0[: int(o0[1].item())].clone()
+    outs = []
+    for k in range(3):
+        for enc_, st in zip(encs, streams):
+            with torch.cuda.stream(st):
+                s = torch.empty(enc_.scan_capacity(w2, h2, 1), dtype=torch.uint8, device="cuda")
+                o = torch.zeros(2, dtype=torch.int64, device="cuda")
+                enc_.encode_device(d2, w2, h2, 1, scan=s, offsets=o)
+                outs.append((s, o))
+    torch.cuda.synchronize()
+    for enc_ in encs:
+        enc_.status()
+    for s, o in outs:
+        n = int(o[1].item())
+        assert n == want.numel() and torch.equal(s[:n], want)
     for enc_ in encs:
         enc_.close()
 
