@@ -1,4 +1,4 @@
-"""Timing experiment: K1/K2 event times versus image size (whole 'rounds' of strips per warp slot)."""
+"""Timing experiment: K1 / K1b / K2 event times versus image size (whole 'rounds' of strips per warp slot)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,5 +20,5 @@ for (w, h) in [(2048, 1184), (2048, 2368), (2048, 4736), (2048, 9472), (2048, 18
     for i in range(64):
         enc.encode_device(ring[i % 4], w, h, 1)
     ev1.record(); torch.cuda.synchronize()
-    print(f"{w}x{h}: strips={strips} rounds={strips/2368:.2f} K1={1e3*t['ms'][0]/32:.1f}us K2={1e3*t['ms'][1]/32:.1f}us "
+    print(f"{w}x{h}: strips={strips} rounds={strips/2368:.2f} K1={1e3*t['ms'][0]/32:.1f}us K1b={1e3*t['ms'][5]/32:.1f}us K2={1e3*t['ms'][1]/32:.1f}us "
           f"stream_step={1e3*ev0.elapsed_time(ev1)/64:.1f}us  {w*h/1e6/(ev0.elapsed_time(ev1)/64*1e-3)/1e3:.0f} Gpx/s", flush=True)
