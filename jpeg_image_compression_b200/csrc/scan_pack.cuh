@@ -236,6 +236,20 @@ k_merge_stuff(const PackArgs a, const int win_words)
                 }
                 if (tail + tid < hi) part += sbits[tail + tid];
             }
+            // the first 64 words of this warp's strips are requested now, together with the bit counts: one global
+            // round trip for both (words beyond a strip's end are ignored below; a slot holds at least 64 words)
+            const uint8_t *tile_streams = a.streams + (strip_base + strip0) * (uint64_t)a.slot_bytes;
+            uint32_t early[K2_TILE_STRIPS / K2_WARPS][2];
+#pragma unroll
+            for (int q = 0; q < K2_TILE_STRIPS / K2_WARPS; ++q) {
+                const uint32_t kk = warp + q * K2_WARPS;
+                early[q][0] = early[q][1] = 0;
+                if (kk < nstrips) {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(tile_streams + kk * (uint64_t)a.slot_bytes);
+                    early[q][0] = src[lane];
+                    early[q][1] = src[lane + 32];
+                }
+            }
             uint32_t fix0 = 0;                                       // bits of the image's first DC symbol (rle.c:68-76)
             if (warp == 0) {
                 uint32_t len = 0;
@@ -297,8 +311,10 @@ k_merge_stuff(const PackArgs a, const int win_words)
             // their last bit (K1b), so nothing has to be masked.
             if (fits) {
                 const uint32_t rel_begin = (uint32_t)(begin - (w0 << 5));         // bit position of the tile's first bit in the window
-                const uint8_t *tile_streams = a.streams + (strip_base + strip0) * (uint64_t)a.slot_bytes;
-                for (uint32_t kk = warp; kk < nstrips; kk += K2_WARPS) {
+#pragma unroll
+                for (int q = 0; q < K2_TILE_STRIPS / K2_WARPS; ++q) {
+                    const uint32_t kk = warp + q * K2_WARPS;
+                    if (kk >= nstrips) break;
                     const uint32_t seg_begin = s_seg_end[kk], len = s_seg_end[kk + 1] - seg_begin;
                     const uint32_t dstbit = rel_begin + seg_begin, sh = dstbit & 31u, nw = (len + 31u) >> 5;
                     const uint32_t *src = reinterpret_cast<const uint32_t *>(tile_streams + kk * (uint64_t)a.slot_bytes);
@@ -306,7 +322,8 @@ k_merge_stuff(const PackArgs a, const int win_words)
                     uint32_t carry = 0;                                           // word i-1 for lane 0
                     for (uint32_t i0 = 0; i0 < nw + 1; i0 += 32) {
                         const uint32_t i = i0 + lane;
-                        const uint32_t cur_w = i < nw ? src[i] : 0u;
+                        uint32_t cur_w = i0 == 0 ? early[q][0] : i0 == 32 ? early[q][1] : (i < nw ? src[i] : 0u);
+                        if (i >= nw) cur_w = 0u;
                         uint32_t prev_w = __shfl_up_sync(0xffffffffu, cur_w, 1);
                         if (lane == 0) prev_w = carry;
                         carry = __shfl_sync(0xffffffffu, cur_w, 31);
