@@ -169,7 +169,7 @@ k_merge_stuff(const PackArgs a, const int win_words)
     __shared__ uint32_t s_seg_end[32];              // inclusive prefix of the segment lengths (bits, relative to the tile's begin), padded with ~0
     __shared__ uint32_t s_seg_raw[2];               // bit counts of the two strips after the tile
     __shared__ uint32_t s_pseudo[2];                // the image's first DC symbol, left-aligned; its length
-    __shared__ uint32_t s_warp[K2_WARPS];
+    __shared__ uint32_t s_warp[K2_WARPS], s_warp_b[K2_WARPS];
     __shared__ uint64_t s_scratch[9];
     __shared__ unsigned long long s_next_tile;
 
@@ -401,43 +401,74 @@ k_merge_stuff(const PackArgs a, const int win_words)
             const uint32_t wlast = (wb1 + 3) >> 2;
             uint8_t *out = a.out + (uint64_t)img * a.out_slot;
             uint64_t round_pos = (w.B0 - origin) + ff_excl;           // output index of the round's first byte
-            // Rounds of four consecutive window words (16 stream bytes) per thread.  The stuffed bytes (huffman.c:26-32)
-            // are laid out in the staging area at the output's 16-byte phase and leave as aligned 128-bit stores;
-            // only the ragged first / last 16-byte unit of a round is written byte by byte.
-            for (uint32_t i0 = (wb0 >> 2) & ~3u; i0 < wlast; i0 += K2_ROUND_WORDS) {
-                const uint32_t i = i0 + 4 * tid;
-                uint32_t v[4];
-                const uint32_t cnt = masked_quad(win, i, wb0, wb1, v);            // beyond wlast: masked off
-                // owned bytes of this thread's group: window bytes [lo, hi)
-                const uint32_t lo = min(max(4u * i, wb0), wb1), hi = max(min(4u * i + 16u, wb1), lo);
-                const uint32_t nb = hi - lo;                                      // owned stream bytes
-                uint32_t incl = (cnt << 16) | nb;                                 // both prefix sums at once (nb, cnt <= 2^15 per round)
+            // Rounds of four consecutive window words (16 stream bytes) per thread and quad; a typical tile (about 680
+            // words, a few 0xFF bytes) is ONE round of two quads per thread, a tile whose stuffed bytes might not fit the
+            // staging area takes rounds of one quad.  The stuffed bytes (huffman.c:26-32) are laid out in the staging area
+            // at the output's 16-byte phase and leave as aligned 128-bit stores; only the ragged first / last 16-byte
+            // unit of a round is written byte by byte.
+            const uint32_t i_start = (wb0 >> 2) & ~3u;
+            const uint32_t Q = (wlast - i_start <= 2u * K2_ROUND_WORDS &&
+                                (uint32_t)(w.B1 - w.B0) + w.tile_ff + 64u <= (uint32_t)(K2_STAGE_BYTES - 32)) ? 2u : 1u;
+            for (uint32_t i0 = i_start; i0 < wlast; i0 += Q * K2_ROUND_WORDS) {
+                uint32_t v[2][4], own[2], incl[2], lo[2], hi[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    own[q] = 0;
+                    lo[q] = hi[q] = 0;
+                    if ((uint32_t)q < Q) {
+                        const uint32_t i = i0 + 4u * ((uint32_t)tid + K2_THREADS * q);
+                        const uint32_t cnt = masked_quad(win, i, wb0, wb1, v[q]);     // beyond wlast: masked off
+                        // owned bytes of this quad: window bytes [lo, hi)
+                        lo[q] = min(max(4u * i, wb0), wb1);
+                        hi[q] = max(min(4u * i + 16u, wb1), lo[q]);
+                        own[q] = (cnt << 16) | (hi[q] - lo[q]);                       // both prefix sums at once (<= 2^13 each per round)
+                    }
+                    incl[q] = own[q];
+                }
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += n;
+                    const uint32_t n0 = __shfl_up_sync(0xffffffffu, incl[0], o), n1 = __shfl_up_sync(0xffffffffu, incl[1], o);
+                    if (lane >= o) {
+                        incl[0] += n0;
+                        incl[1] += n1;
+                    }
                 }
-                if (lane == 31) s_warp[warp] = incl;
+                if (lane == 31) {
+                    s_warp[warp] = incl[0];
+                    s_warp_b[warp] = incl[1];
+                }
                 __syncthreads();
-                uint32_t before = incl - ((cnt << 16) | nb), round_total = 0;
+                uint32_t before[2] = {incl[0] - own[0], incl[1] - own[1]}, total0 = 0, total1 = 0;
 #pragma unroll
                 for (int ww = 0; ww < K2_WARPS; ++ww) {
-                    const uint32_t ws = s_warp[ww];
-                    if (ww < warp) before += ws;
-                    round_total += ws;
+                    const uint32_t wa = s_warp[ww], wb_ = s_warp_b[ww];
+                    if (ww < warp) {
+                        before[0] += wa;
+                        before[1] += wb_;
+                    }
+                    total0 += wa;
+                    total1 += wb_;
                 }
+                before[1] += total0;                                              // the second quads follow all first quads
+                const uint32_t round_total = total0 + total1;
                 const uint32_t round_bytes = (round_total & 0xFFFFu) + (round_total >> 16);   // stuffed bytes of this round
                 const uint32_t phase = (uint32_t)((uintptr_t)(out + round_pos) & 15u);
-                uint32_t rel = phase + (before & 0xFFFFu) + (before >> 16);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int q = 0; q < 2; ++q) {
+                    if ((uint32_t)q < Q) {
+                        const uint32_t i = i0 + 4u * ((uint32_t)tid + K2_THREADS * q);
+                        uint32_t rel = phase + (before[q] & 0xFFFFu) + (before[q] >> 16);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) {
-                        const uint32_t b = 4u * (i + j) + kb;
-                        if (b >= lo && b < hi) {
-                            const uint32_t byte = (v[j] >> (24 - 8 * kb)) & 0xFFu;
-                            stage[rel++] = (uint8_t)byte;
-                            if (byte == 0xFFu) stage[rel++] = 0;                  // huffman.c:29-31
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int kb = 0; kb < 4; ++kb) {
+                                const uint32_t b = 4u * (i + j) + kb;
+                                if (b >= lo[q] && b < hi[q]) {
+                                    const uint32_t byte = (v[q][j] >> (24 - 8 * kb)) & 0xFFu;
+                                    stage[rel++] = (uint8_t)byte;
+                                    if (byte == 0xFFu) stage[rel++] = 0;          // huffman.c:29-31
+                                }
+                            }
                         }
                     }
                 }
@@ -457,7 +488,7 @@ k_merge_stuff(const PackArgs a, const int win_words)
                     }
                 }
                 round_pos += round_bytes;
-                __syncthreads();                                                  // staging area and s_warp are reused
+                __syncthreads();                                                  // staging area and the warp sums are reused
             }
             {   // the window is handed back zeroed
                 uint4 *wq = reinterpret_cast<uint4 *>(k2_smem_words + (cur ^ 1) * win_words);
