@@ -2,11 +2,14 @@
 //
 // Batch driver next to the drop-in 2-argument CLI: every input goes
 // BMP file -> pinned host buffer -> jpegb200_encode_bmp_to_jpeg_host (pixel array read in place
-// on the device, complete JPEG file back) -> <out_dir>/<name>.jpg.  Two worker threads, each with
+// on the device, complete JPEG file back) -> <out_dir>/<name>.jpg.  Two worker threads per GPU, each with
 // its own encoder handle and CUDA stream, so one image's PCIe copy overlaps the other's kernels
-// and file I/O.  Output files are byte-identical to jpeg_compression_app's.
+// and file I/O; files are dealt round-robin to the workers, i.e. the batch is sharded by image across
+// all visible B200s (JPEGB200_DEVICE=<n> pins it to one, JPEGB200_BATCH_GPUS=<k> limits the count).
+// Output files are byte-identical to jpeg_compression_app's.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -50,13 +53,16 @@ int main(int argc, char **argv)
     }
     const std::string dir = argv[1];
     std::vector<std::string> files(argv + 2, argv + argc);
-    int device = 0;
-    if (const char *e = getenv("JPEGB200_DEVICE")) device = atoi(e);
-    const int nthreads = files.size() > 1 ? 2 : 1;
+    int first_device = 0, ngpus = jpegb200_device_count();
+    if (const char *e = getenv("JPEGB200_DEVICE")) { first_device = atoi(e); ngpus = 1; }
+    if (const char *e = getenv("JPEGB200_BATCH_GPUS")) ngpus = std::max(1, std::min(ngpus, atoi(e)));
+    if (ngpus < 1) ngpus = 1;                                  // no device: the workers report the error
+    const int nthreads = (int)std::max<size_t>(1, std::min<size_t>(files.size(), (size_t)2 * ngpus));
     std::vector<int> failed(nthreads, 0);
     std::vector<double> mpix(nthreads, 0.0);
     const auto t0 = std::chrono::steady_clock::now();
     auto worker = [&](int t) {
+        const int device = first_device + t % ngpus;
         cudaSetDevice(device);
         jpegb200_encoder *enc = jpegb200_encoder_create(device);
         if (!enc) {
@@ -111,7 +117,7 @@ int main(int argc, char **argv)
     int bad = 0;
     double mp = 0;
     for (int t = 0; t < nthreads; ++t) { bad += failed[t]; mp += mpix[t]; }
-    printf("Encoded %zu of %zu files, %.1f Mpixel in %.3f s (%.1f Mpixel/s incl. file I/O and CUDA start-up)\n",
-           files.size() - bad, files.size(), mp, sec, mp / sec);
+    printf("Encoded %zu of %zu files, %.1f Mpixel in %.3f s (%.1f Mpixel/s incl. file I/O and CUDA start-up; %d GPU%s, %d workers)\n",
+           files.size() - bad, files.size(), mp, sec, mp / sec, ngpus, ngpus == 1 ? "" : "s", nthreads);
     return bad ? 1 : 0;
 }
