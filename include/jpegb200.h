@@ -150,9 +150,10 @@ enum {
     JPEGB200_ERR_INTERNAL = 5
 };
 
-/* dct_mode: 0 = fast separable DCT + rigorous guard band + exact re-evaluation of
- * flagged coefficients (default, bit-exact by construction); 1 = every coefficient
- * in the reference's exact summation order (slow, used to cross-check mode 0). */
+/* dct_mode: 0 = transform on the tensor cores (exact integer limb sums of the reference's LUT products) + rigorous
+ * guard band + exact re-evaluation of flagged coefficients (default, bit-exact by construction); 1 = every
+ * coefficient in the reference's exact summation order (slow, used to cross-check mode 0); 2 = register butterfly
+ * transform + guard band + exact re-evaluation (the round-1 transform, same output, kept for comparison). */
 int          jpegb200_device_count(void);
 const char  *jpegb200_last_error(void);
 jpegb200_encoder *jpegb200_encoder_create(int device);
@@ -209,14 +210,15 @@ typedef struct {
 int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out);
 
 /* Per-kernel device time: with profiling on, every kernel launch is bracketed by cudaEvents
- * on the launching stream.  kernel ids: 0 fused block kernel (K1), 1 scan+pack+stuff (K2),
- * 2 batch layout, 3 batch compaction.  Synchronises the device. */
+ * on the launching stream.  kernel ids: 0 block kernel (K1), 1 merge + stuff (K2), 2 batch layout,
+ * 3 batch compaction, 4 file framing, 5 strip entropy kernel (K1b).  Synchronises the device. */
 int jpegb200_encoder_set_profiling(jpegb200_encoder *enc, int on);
 int jpegb200_encoder_kernel_times(jpegb200_encoder *enc, double ms_total[8], uint64_t calls[8], int reset);
 
 /* Host buffers in, host buffers out (the reference-facing call with an explicit handle):
- * H2D copy of the RGB payload, the four kernels, D2H copy of the stuffed scan.  Pinned caller
- * buffers make the copies run at PCIe speed.  Synchronous. */
+ * H2D copy of the RGB payload, the three kernels, D2H copy of the stuffed scan (copied speculatively at the size of
+ * the previous result, so that the call needs ONE stream synchronisation).  Pinned caller buffers make the copies
+ * run at PCIe speed.  Synchronous. */
 int jpegb200_encode_host(jpegb200_encoder *enc, const uint8_t *host_rgb, int width, int height,
                          uint8_t *host_scan, uint64_t host_capacity, uint64_t *host_scan_bytes,
                          void *cuda_stream);
