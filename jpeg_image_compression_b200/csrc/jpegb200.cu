@@ -211,7 +211,7 @@ struct jpegb200_encoder {
     uint64_t lookback_words = 0;
     uint64_t total_blocks = 0;      // blocks K1 produced (all images, incl. stripe halo)
     uint64_t launches = 0;
-    int k2_ctas_per_sm[2] = {0, 0};
+    int k2_ctas_per_sm[2] = {0, 0};   // [0] resident merge-kernel CTAs per SM, [1] the slot size that was computed for
     int k1_grid = 0, k1_warps = 0;   // shape of the last K1 launch
     bool stripe_ready = false;
     bool stripe_state_fresh = false;   // K2's look-back state is still the zeroed one K1 left (no memset before the first stripe encode)
@@ -509,12 +509,12 @@ static int launch_entropy(jpegb200_encoder *enc, cudaStream_t st)
 {
     const PackArgs &a = enc->args;
     const int smem = k2_smem((int)enc->slot_bytes), win_words = k2_win_words((int)enc->slot_bytes);
-    const bool small = enc->slot_bytes <= (uint32_t)STREAM_SMALL_BYTES;
-    int &per_sm = enc->k2_ctas_per_sm[small ? 0 : 1];
-    if (per_sm == 0) {
-        int n = 0;         // occupancy at the largest window of the class
-        JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff, K2_THREADS, k2_smem(small ? STREAM_SMALL_BYTES : STREAM_BIG_BYTES)));
+    int &per_sm = enc->k2_ctas_per_sm[0];
+    if (per_sm == 0 || enc->k2_ctas_per_sm[1] != (int)enc->slot_bytes) {     // occupancy at this launch's window size
+        int n = 0;
+        JB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_merge_stuff, K2_THREADS, smem));
         per_sm = n > 0 ? n : 1;
+        enc->k2_ctas_per_sm[1] = (int)enc->slot_bytes;
     }
     const uint64_t total = (uint64_t)a.tiles * (uint64_t)a.count;
     unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)enc->sm_count * per_sm);

@@ -161,7 +161,7 @@ struct PendingTile {
 
 // The windows are sized at launch (dynamic shared memory): K2_TILE_STRIPS x the strip slot size.  An image that needs
 // bigger slots raises ERRBIT_WORKSPACE in K1 and the caller re-runs both kernels with a larger bytes_per_block.
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(K2_THREADS, 7)
 k_merge_stuff(const PackArgs a, const int win_words)
 {
     extern __shared__ __align__(16) uint32_t k2_smem_words[];   // two windows, then the output staging area
