@@ -567,7 +567,8 @@ static int encode_launch(jpegb200_encoder *enc, uint8_t *d_scan, uint64_t scan_c
         }
         {
             TimedLaunch t(enc, st, KID_COMPACT);
-            const unsigned gx = (unsigned)std::min<uint64_t>((a.out_slot / 16 + 255) / 256, 64);
+            // 16 bytes per thread and iteration; a slot is sized for the worst case, typical images fill a ninth of it
+            const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((a.out_slot / 128 + 255) / 256, 32));
             k_compact<<<dim3(gx, (unsigned)a.count), 256, 0, st>>>(a.out, a.out_slot, a.image_bytes, d_scan_offsets, d_scan,
                                                                    scan_capacity, lead);
         }

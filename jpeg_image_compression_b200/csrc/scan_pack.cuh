@@ -549,8 +549,8 @@ k_layout(const uint64_t *__restrict__ image_bytes, uint64_t *__restrict__ scan_o
 }
 
 // batch mode: move every image's stuffed bytes from its (16-byte aligned) slot to its final, arbitrarily
-// aligned offset.  Destination-aligned 32-bit stores; the source is read as aligned words and realigned
-// with a funnel shift; the few head / tail bytes are copied one by one.
+// aligned offset.  Destination-aligned 128-bit stores; the source is read as aligned words and realigned
+// with funnel shifts; the few head / tail bytes are copied one by one.
 __global__ void __launch_bounds__(256)
 k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const uint64_t *__restrict__ image_bytes,
           const uint64_t *__restrict__ scan_offsets, uint8_t *__restrict__ scan, const uint64_t scan_capacity,
@@ -561,15 +561,20 @@ k_compact(const uint8_t *__restrict__ slots, const uint64_t slot_stride, const u
     if (scan_offsets[img + 1] > scan_capacity) return;           // flagged by k_layout
     const uint8_t *src = slots + (uint64_t)img * slot_stride;
     uint8_t *dst = scan + dst0;
-    const uint64_t head = min(n, (uint64_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));   // bytes up to dst alignment
-    const uint64_t nwords = (n - head) >> 2, tail0 = head + nwords * 4;
+    const uint64_t head = min(n, (uint64_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u));   // bytes up to dst alignment
+    const uint64_t nvec = (n - head) >> 4, tail0 = head + nvec * 16;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
     if (tid < head) dst[tid] = src[tid];
     if (tid < n - tail0) dst[tail0 + tid] = src[tail0 + tid];
-    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
-    const uint32_t sh = (uint32_t)head * 8u;                     // src word phase relative to dst words (head < 4)
-    for (uint64_t j = tid; j < nwords; j += nthreads) d32[j] = __funnelshift_r(s32[j], s32[j + 1], sh);
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src) + (head >> 2);   // source word that holds byte `head`
+    uint4 *d128 = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t sh = (uint32_t)(head & 3u) * 8u;              // byte phase of the source inside its word
+    for (uint64_t j = tid; j < nvec; j += nthreads) {
+        const uint32_t *p = s32 + 4 * j;
+        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = sh ? p[4] : 0u;
+        d128[j] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                             __funnelshift_r(w3, w4, sh));
+    }
 }
 
 // files mode: frame every image's scan with the JFIF header (jpeg_handler.c:220-233; the 328 bytes are
