@@ -326,7 +326,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     scan_bytes = [int(o[per_step].item()) for _, o in outs]
 
     # ---- CUDA graphs that together hold exactly K steps ---------------------------------------------
-    def capture(n_streams, nsteps):
+    def capture(n_streams, nsteps, handles=None):
+        handles = handles or encs
         side = [torch.cuda.Stream() for _ in range(n_streams)]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -340,7 +341,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 for j, s_ in enumerate(side):
                     with torch.cuda.stream(s_):
                         for i in range(j, nsteps, n_streams):
-                            step(i, encs[j])
+                            step(i, handles[j])
                 for s_ in side:
                     main.wait_stream(s_)
         return g
@@ -349,14 +350,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     glen = _graph_len(args.steps)
     full, rest = divmod(args.steps, glen)
 
-    def make_runner(n_streams):
+    def make_runner(n_streams, handles=None):
         if not use_graph:
             def eager(n=args.steps):
                 for i in range(n):
-                    step(i, encs[i % n_streams] if n_streams > 1 else None)
+                    step(i, (handles or encs)[i % n_streams] if n_streams > 1 else None)
             return eager
-        g_main = capture(n_streams, glen)
-        g_rest = capture(n_streams, rest) if rest else None
+        g_main = capture(n_streams, glen, handles)
+        g_rest = capture(n_streams, rest, handles) if rest else None
 
         def run_k():
             for _ in range(full):
@@ -399,6 +400,34 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if use_graph and nstreams > 1:                          # for the record: strictly serial encodes
         run_1 = make_runner(1)
         single_stream_ms = timed(run_1, repeats) / timed_steps
+
+    # ---- the same workload with the library's concurrency hint: 16 handles, each sized for its share of the SMs ----
+    shared_device = None
+    if args.workload == "uhd4k" and use_graph and not args.no_shared_device:
+        n_sh = 16
+        sh_encs = [jb.DeviceEncoder(local_rank) for _ in range(n_sh)]
+        for e in sh_encs:
+            e.set_concurrency(n_sh)
+            for i in range(ring):
+                step(i, e)
+        torch.cuda.synchronize()
+        for e in sh_encs:
+            e.status()
+        sh_ring = [bytes(outs[k][0][: int(outs[k][1][per_step].item())].cpu().numpy().tobytes()) for k in range(min(ring, 2))]
+        for k in range(min(ring, 2)):                       # the hint must not change a byte
+            step(k, enc)
+        torch.cuda.synchronize()
+        same = all(sh_ring[k] == outs[k][0][: int(outs[k][1][per_step].item())].cpu().numpy().tobytes() for k in range(min(ring, 2)))
+        run_sh = make_runner(n_sh, sh_encs)
+        ms_sh = max_over_ranks(timed(run_sh, repeats))
+        for e in sh_encs:
+            e.status()
+        shared_device = {"value": round(px_step * timed_steps * world / (ms_sh * 1e-3) / 1e6, 1), "unit": UNIT,
+                         "encoder_streams": n_sh, "concurrency_hint": n_sh, "steps": timed_steps,
+                         "bytes_equal_to_default_launch_shape": bool(same),
+                         "note": "jpegb200_encoder_set_concurrency(16): every launch sized for ~0.3 of the SMs; "
+                                 "the headline value keeps the default (whole-device) launch shape"}
+        del run_sh, sh_encs
 
     # ---- sensitivity rows of SURVEY.md 8(d): the same workload at amp=0 (smooth) and amp=64 (entropy-heavy) ----
     sensitivity = None
@@ -704,7 +733,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "cuda_graph": bool(use_graph), "graph_steps": glen if use_graph else None,
                        "scan_bytes_per_step": int(mean_scan), "encoder_streams": nstreams,
                        "single_stream_ms_per_step": round(single_stream_ms, 5) if single_stream_ms else None,
-                       "sensitivity": sensitivity, "extra": extra},
+                       "shared_device": shared_device, "sensitivity": sensitivity, "extra": extra},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * timed_steps),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
@@ -730,6 +759,7 @@ def main():
     ap.add_argument("--no-giga", action="store_true", help="skip the 32768x32768 stripe row of config.extra")
     ap.add_argument("--extra-images", type=int, default=4096, help="total images of the strong-scaling batch row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shared-device", action="store_true", help="skip the 16-handle concurrency-hint row")
     ap.add_argument("--no-sensitivity", action="store_true", help="skip the amp=0 / amp=64 rows")
     args = ap.parse_args()
     if args.impl == "reference":

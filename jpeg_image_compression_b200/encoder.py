@@ -32,6 +32,10 @@ class DeviceEncoder:
         self._scan = None
         self._offsets = None
 
+    def set_concurrency(self, handles: int) -> None:
+        """Launch-shape hint (include/jpegb200.h): `handles` encoders are kept busy side by side on this GPU."""
+        check(self.lib.jpegb200_encoder_set_concurrency(self.handle, int(handles)), "set_concurrency")
+
     def close(self):
         if self.handle:
             self.lib.jpegb200_encoder_destroy(self.handle)

@@ -620,3 +620,25 @@ def test_tensor_map_path_edges(enc, oracle):
     scans = enc.encode_batch(imgs)
     for i in range(6):
         assert scans[i] == oracle.encode_scan(imgs[i]), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("handles", [2, 8, 16, 64])
+def test_concurrency_hint_does_not_change_bytes(handles):
+    """jpegb200_encoder_set_concurrency only reshapes the launches (fewer CTAs, more work per CTA): same scan bytes
+    for a single image, a ragged one and a batch."""
+    import torch
+    base = jb.DeviceEncoder(0)
+    hinted = jb.DeviceEncoder(0)
+    hinted.set_concurrency(handles)
+    for (w, h, n) in [(3840, 2160, 1), (1001, 777, 1), (640, 480, 5)]:
+        rgb = base.synth(w, h, n, 7, 20)
+        a_scan, a_off = base.encode_device(rgb, w, h, n)
+        torch.cuda.synchronize()
+        a_off = a_off.cpu().numpy().copy()
+        a = a_scan[: int(a_off[n])].cpu().numpy().tobytes()
+        b_scan, b_off = hinted.encode_device(rgb, w, h, n)
+        torch.cuda.synchronize()
+        b_off = b_off.cpu().numpy()
+        assert (a_off[: n + 1] == b_off[: n + 1]).all()
+        assert a == b_scan[: int(b_off[n])].cpu().numpy().tobytes()

@@ -7,7 +7,7 @@ import json,sys
 for l in open(sys.argv[1]):
     l=l.strip()
     if l.startswith('{'):
-        d=json.loads(l); print(sys.argv[2], d.get('value'), d.get('ms_per_step'), d['roofline'].get('per_kernel_ms'), d['roofline'].get('frac'), d['config'].get('single_stream_ms_per_step'))
+        d=json.loads(l); print(sys.argv[2], d.get('value'), d.get('ms_per_step'), d['roofline'].get('per_kernel_ms'), d['roofline'].get('frac'), d['config'].get('single_stream_ms_per_step'), d['config'].get('shared_device'))
 PY
 }
 run 4k timeout 300 $B --steps 240 --warmup 24
