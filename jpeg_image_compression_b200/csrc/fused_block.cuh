@@ -138,14 +138,14 @@ __device__ __forceinline__ StripCtx strip_ctx(const Geom &g, const StripPos &p)
 // through the warp's mbarrier.  Each row copy starts at the row's 16-byte-aligned address and covers whole 16-byte
 // chunks, so any width / base alignment works.  Also records the rows' 16-byte phases in c.mispack.  Must be called
 // by the whole warp.
-__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane, const CUtensorMap *tmap)
+__device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uint64_t *bar, int lane, const CUtensorMap *tmap, bool fenced = false)
 {
     if (tmap) {
         // aligned input: ONE tensor-map copy of the 8 x 768-byte box (rows and columns beyond the image are
         // zero-filled and never used: the luma pass clamps the row and stops at the last real pixel)
         c.mispack = 0;
         if (lane == 0) {
-            fence_proxy_async();
+            if (!fenced) fence_proxy_async();
             mbar_expect_tx(bar, 8 * TMAP_ROW_BYTES);
             tensor_g2s_3d(raw, tmap, c.tx, c.ty, c.tz, bar);
         }
@@ -157,7 +157,7 @@ __device__ __forceinline__ void strip_issue_loads(StripCtx &c, uint8_t *raw, uin
     const uint32_t bytes = lane < 8 ? (mis + 3u * (uint32_t)c.npx + 15u) & ~15u : 0u;     // <= 784
     c.mispack = __reduce_or_sync(0xffffffffu, lane < 8 ? mis << (4 * r) : 0u);
     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-    fence_proxy_async();                                 // the tile was just read through the generic proxy
+    if (!fenced) fence_proxy_async();                    // the tile was just read through the generic proxy
     if (lane == 0) mbar_expect_tx(bar, total);
     __syncwarp();
     if (lane < 8) bulk_g2s(raw + r * RAW_PITCH, row - mis, bytes, bar);
@@ -171,6 +171,20 @@ __device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2,
     const uint32_t y2 = __dp4a(__byte_perm(w1, w2, 0x0432u), wt_lo, 0u);
     const uint32_t y3 = __dp4a(w2, wt_hi, 0u);
     return __byte_perm(__byte_perm(y0, y1, 0x0051u), __byte_perm(y2, y3, 0x0051u), 0x5410u);
+}
+
+// luma of two pixels (each in the weighted bytes of one word) as the fp16 pair {1024 + Y0, 1024 + Y1}: the DP4A
+// accumulator 0x64000000 puts 0x64 above the 16-bit sum whose high byte is Y
+__device__ __forceinline__ uint32_t luma2_half(uint32_t a, uint32_t b, uint32_t wa, uint32_t wb)
+{
+    return __byte_perm(__dp4a(a, wa, 0x64000000u), __dp4a(b, wb, 0x64000000u), 0x7531u);
+}
+
+__device__ __forceinline__ uint32_t half2_sub1152(uint32_t h)
+{
+    uint32_t r;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h), "r"(0xE480E480u));
+    return r;
 }
 
 // four luma bytes -> four level-shifted fp16 values (converter.c:84): 0x64yy is the fp16 1024 + yy, and subtracting
@@ -328,8 +342,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     constexpr int WARPS = Cfg::WARPS;
 #ifdef JPEGB200_TRACE   // tracing build only (make trace -> libjpegb200_trace.so)
 #define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
+// phases of the warp's 4th tile (steady state): third region of the trace buffer
+#define K1_TRACE_TILE(slot) do { if (trace && lane == 0 && trace_it == 3u) trace[(uint64_t)(2u * stride + blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
 #else
 #define K1_TRACE(slot) do { } while (0)
+#define K1_TRACE_TILE(slot) do { } while (0)
 #endif
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -339,6 +356,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     uint8_t *ybuf = raw + RAW_BYTES;
     __shared__ __align__(8) uint64_t s_bar[WARPS + 1 + 4];       // per-warp tile barriers, the table barrier, per-group MMA barriers
     __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_arrive[4];                             // per group: warps that have finished the tile's luma pass (wraps at 4)
     __shared__ float s_cos[64];                                  // the reference's cosine LUT (exact re-evaluation)
     __shared__ __align__(16) float s_scratch[WARPS][64];         // per warp: the 64 products of one re-evaluated coefficient
 
@@ -359,6 +377,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
             for (int i = 0; i < Cfg::GROUPS; ++i) mbar_init(&s_bar[WARPS + 1 + i], 1);
     }
     if (threadIdx.x < 64) s_cos[threadIdx.x] = c_ref_cos[threadIdx.x];
+    if (threadIdx.x < 4) s_arrive[threadIdx.x] = 0u;
     mbar_fence_init();
     __syncwarp();
     // The first strip's pixels are requested before the block-wide set-up below (TMEM allocation, barrier): a warp only
@@ -403,32 +422,50 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     float magic;                                     // 1.5 * 2^23 held in a register: leaves the FFMA's
     asm("mov.f32 %0, 0f4B400000;" : "=f"(magic));     // constant-bank slot to the quantizer constant
 
+#ifdef JPEGB200_TRACE
+    uint32_t trace_it = 0xFFFFFFFFu;
+#endif
     for (; tile_s0 < total; tile_s0 += stride, s += stride) {
+#ifdef JPEGB200_TRACE
+        ++trace_it;
+#endif
         const bool valid = s < total;                            // TC: the last tile may have idle warps
         StripCtx me = cur;
         uint32_t yw[16];                                         // the lane's 64 luma bytes (TC)
-        uint32_t absdev = 0, absmean = 0;                        // A = sum |Y - 128|, Ac = sum |Y - mean|
+        uint32_t absdev = 0, absmean = 0, sumy = 0;              // A = sum |Y - 128|, Ac = sum |Y - mean|, sum Y
         float x00 = 0.0f;                                        // sum (Y - 128), exact
+        const bool fast = cur.npx == 256 && (cur.mispack & 0x77777777u) == 0u;   // (warp-uniform)
         if (valid) {
+            K1_TRACE_TILE(0);
             mbar_wait(bar, phase);
             phase ^= 1u;
             K1_TRACE(2);
+            K1_TRACE_TILE(1);
 
             // ---- luma pass -> 256 x 8 Y tile ----------------------------------------------------
-            if (cur.npx == 256 && (cur.mispack & 0x33333333u) == 0u) {
-                // full strip, word-aligned rows: 3 LDS + DP4A/PRMT per 4 pixels.  Two rows per trip, not fully
-                // unrolled: the kernel's hot loop has to stay inside the 32 KB instruction cache (L1.5)
+            if (fast) {
+                // full strip, 8-byte aligned rows: lane = block.  Per row 24 bytes (three LDS.64) -> 8 DP4A (two of the
+                // three inputs re-aligned by PRMT; accumulator 0x64000000, so byte 3 of every sum is the fp16 exponent
+                // of 1024 and byte 1 is Y) -> 4 PRMT to fp16 pairs 1024 + Y -> 4 HADD2 (-1152) -> one STS.128 into the
+                // A operand; the Y bytes for the statistics and the re-evaluation path cost 2 more PRMT.  Two rows per
+                // trip, not fully unrolled: the kernel's hot loop has to stay inside the 32 KB instruction cache (L1.5)
 #pragma unroll 2
                 for (int r = 0; r < 8; ++r) {
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(raw + min(r, cur.rmax) * raw_pitch + ((cur.mispack >> (4 * r)) & 12u)) + 3 * lane;
-                    uint32_t *yo = reinterpret_cast<uint32_t *>(ybuf + r * Y_PITCH);
-                    const uint32_t ya = luma4(rw[0], rw[1], rw[2], g.wt_lo, g.wt_hi), yb = luma4(rw[96], rw[97], rw[98], g.wt_lo, g.wt_hi);
-                    yo[lane] = ya;
-                    yo[lane + 32] = yb;
+                    const uint2 *rw = reinterpret_cast<const uint2 *>(raw + min(r, cur.rmax) * raw_pitch + ((cur.mispack >> (4 * r)) & 8u)) + 3 * lane;
+                    const uint2 q0 = rw[0], q1 = rw[1], q2 = rw[2];
+                    const uint32_t p01 = luma2_half(q0.x, __byte_perm(q0.x, q0.y, 0x0543u), g.wt_lo, g.wt_lo);
+                    const uint32_t p23 = luma2_half(__byte_perm(q0.y, q1.x, 0x0432u), q1.x, g.wt_lo, g.wt_hi);
+                    const uint32_t p45 = luma2_half(q1.y, __byte_perm(q1.y, q2.x, 0x0543u), g.wt_lo, g.wt_lo);
+                    const uint32_t p67 = luma2_half(__byte_perm(q2.x, q2.y, 0x0432u), q2.y, g.wt_lo, g.wt_hi);
+                    const uint2 yv = make_uint2(__byte_perm(p01, p23, 0x6420u), __byte_perm(p45, p67, 0x6420u));
+                    *reinterpret_cast<uint2 *>(ybuf + r * Y_PITCH + 8 * lane) = yv;
                     if (TC) {
-                        uint8_t *ap = a_warp + ((lane >> 4) << 10) + (r << 7) + (((lane >> 1) & 7) << 4) + ((lane & 1) << 3);
-                        *reinterpret_cast<uint2 *>(ap) = y4_to_half4(ya);
-                        *reinterpret_cast<uint2 *>(ap + 2048) = y4_to_half4(yb);
+                        absdev = __vsadu4(yv.x, 0x80808080u) + absdev;
+                        absdev = __vsadu4(yv.y, 0x80808080u) + absdev;
+                        sumy = __vsadu4(yv.x, 0u) + sumy;
+                        sumy = __vsadu4(yv.y, 0u) + sumy;
+                        *reinterpret_cast<uint4 *>(a_warp + ((lane >> 3) << 10) + (r << 7) + ((lane & 7) << 4)) =
+                            make_uint4(half2_sub1152(p01), half2_sub1152(p23), half2_sub1152(p45), half2_sub1152(p67));
                     }
                 }
             } else {
@@ -450,9 +487,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                 }
             }
             __syncwarp();
+            K1_TRACE_TILE(2);
 
-            // raw tile is free: prefetch the next strip while this one is transformed
-            if (s + stride < total) {
+            // raw tile is free: prefetch the next strip while this one is transformed (TC: right after the arrival below,
+            // so that the group's MMA is not held up by the address arithmetic)
+            if (!TC && s + stride < total) {
                 strip_advance(g, pos, dq, dr);
                 cur = strip_ctx(g, pos);
                 strip_issue_loads(cur, raw, bar, lane, tmap);
@@ -481,8 +520,14 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
         if (TC) {
             if (valid) fence_proxy_async();                      // the luma pass wrote this warp's quarter of A (generic proxy -> MMA)
             tc_fence_before_sync();
-            named_bar_sync(1 + group, 128);                      // the tile's four A quarters are in shared memory
-            if (quad == 0 && lane == 0) {
+            // The tile's four A quarters are in shared memory (and the group's loads of the previous accumulator are
+            // done) once all four warps have passed this point.  No warp waits here: each bumps the group's arrival
+            // counter (release), and the one that finds the other three already there (acquire) issues the MMA.
+            __syncwarp();
+            uint32_t arrived = 0;
+            if (lane == 0)
+                asm volatile("atom.acq_rel.cta.shared::cta.inc.u32 %0, [%1], 3;" : "=r"(arrived) : "r"(smem_u32(&s_arrive[group])) : "memory");
+            if (arrived == 3u) {
                 mbar_wait(table_bar, 0);                       // the limb matrix (immediate after the first tile)
                 tc_fence_after_sync();
                 const uint32_t b_sa = smem_u32(smem), a_sa = b_sa + K1_BMAT_BYTES + (uint32_t)(group * Cfg::A_TILE_BYTES);
@@ -491,18 +536,27 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                     umma_f16_ss(tmem_d, umma_desc(a_sa + 256u * ks, 128u, 1024u), umma_desc(b_sa + 4096u * ks, 128u, 256u), TC_IDESC, ks > 0 ? 1u : 0u);
                 umma_commit(mma_bar);
             }
+            if (valid && s + stride < total) {                   // prefetch: the fence above also covers the reads of the raw tile
+                strip_advance(g, pos, dq, dr);
+                cur = strip_ctx(g, pos);
+                strip_issue_loads(cur, raw, bar, lane, tmap, /*fenced=*/true);
+            }
+            K1_TRACE_TILE(3);
             if (valid) {
-                // block statistics from the Y bytes while the MMA runs: A = sum |Y - 128|, sum Y, Ac = sum |Y - mean|
-                uint32_t sumy = 0;
+                // block statistics from the Y bytes while the MMA runs: A = sum |Y - 128| and sum Y (the full-strip luma
+                // pass has accumulated them already), Ac = sum |Y - mean|
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const uint2 v = *reinterpret_cast<const uint2 *>(yblk + r * Y_PITCH);
                     yw[2 * r] = v.x;
                     yw[2 * r + 1] = v.y;
-                    absdev = __vsadu4(v.x, 0x80808080u) + absdev;
-                    absdev = __vsadu4(v.y, 0x80808080u) + absdev;
-                    sumy = __vsadu4(v.x, 0u) + sumy;
-                    sumy = __vsadu4(v.y, 0u) + sumy;
+                }
+                if (!fast) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        absdev = __vsadu4(yw[j], 0x80808080u) + absdev;
+                        sumy = __vsadu4(yw[j], 0u) + sumy;
+                    }
                 }
                 x00 = (float)((int)sumy - 8192);
                 {
@@ -511,8 +565,10 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
 #pragma unroll
                     for (int j = 0; j < 16; ++j) absmean = __vsadu4(yw[j], m4) + absmean;
                 }
+                K1_TRACE_TILE(4);
                 mbar_wait(mma_bar, mma_phase);
                 tc_fence_after_sync();
+                K1_TRACE_TILE(5);
                 // guard half-width in fixed-point units
                 const float eb = fminf((float)absdev * kTcGamma, fmaf((float)absdev, kTcGammaA, fmaf((float)absmean, kTcGammaC, kTcGamma0)));
                 const f32x2 e2 = pack2(eb, eb), k2048 = pack2(2048.0f, 2048.0f), m2 = pack2(magic, magic);
@@ -540,7 +596,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                         xw[4 * c + wi] = (h ^ l) | xforce;
                     }
                 }
-                tc_fence_before_sync();                          // orders these loads before the next tile's MMA (through the group barrier)
+                tc_fence_before_sync();                          // orders these loads before the next tile's MMA (through the arrival counter)
+                K1_TRACE_TILE(6);
             }
             mma_phase ^= 1u;
         } else if (valid) {
@@ -670,9 +727,16 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
         if (lane < me.vb) {
             uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 64);
 #pragma unroll
+#ifdef JB_EXPERIMENT_HALFSTORE
+            for (int i = 0; i < 2; ++i) dst[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
+#elif defined(JB_EXPERIMENT_NOSTORE)
+            if (zw[5] == 0x12345678u) dst[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+#else
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
+#endif
         }
         __syncwarp();                                            // the Y tile is rewritten by the next strip's luma pass
+        K1_TRACE_TILE(7);
 #ifdef JPEGB200_TRACE
         // second half of the trace buffer: completion times of this warp's first 8 strips
         if (trace && lane == 0) {
@@ -692,6 +756,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
     }
 #endif
 #undef K1_TRACE
+#undef K1_TRACE_TILE
     if (flagged_counter) {
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 8);

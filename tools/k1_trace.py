@@ -22,10 +22,11 @@ grid, wpc = ctypes.c_int(0), ctypes.c_int(0)
 check(enc.lib.jpegb200_encoder_launch_shape(enc.handle, ctypes.byref(grid), ctypes.byref(wpc)), "launch_shape")
 nwarps = grid.value * wpc.value
 print("block kernel grid", grid.value, "x", wpc.value, "warps")
-tr = np.zeros((2 * nwarps, 8), np.uint64)
-check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, 2 * nwarps), "trace")
+tr = np.zeros((3 * nwarps, 8), np.uint64)
+check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, 3 * nwarps), "trace")
 t = tr[:nwarps].astype(np.int64)
-ends = tr[nwarps:].astype(np.int64)
+ends = tr[nwarps:2 * nwarps].astype(np.int64)
+detail = tr[2 * nwarps:].astype(np.int64)
 t0 = t[:, 0].min()
 names = ["entry", "prologue", "tile0", "-", "-", "-", "exit"]
 print("warps", nwarps, "strips", strips, "span us", (t[:, 6].max() - t0) / 1e3)
@@ -56,3 +57,15 @@ for it in range(8):
     dur = (col[okk] - prev[okk]) / 1e3
     print(f"strip {it}: n={okk.sum():5d} duration median {np.median(dur):5.2f} p90 {np.percentile(dur, 90):5.2f} max {dur.max():5.2f}  (ends at median {np.median((col[okk] - t0) / 1e3):6.2f})")
     prev = col
+
+# phases of every warp's 4th tile (steady state on large inputs)
+ok = (detail > 0).all(axis=1)
+if ok.any():
+    d = detail[ok]
+    names = ["wait for pixels", "luma pass", "prefetch+arrive(+MMA issue)", "statistics", "wait for MMA", "TMEM loads + quantization", "flag pass + stores"]
+    print(f"4th tile of {ok.sum()} warps, phase durations in us:")
+    for i, n in enumerate(names):
+        x = (d[:, i + 1] - d[:, i]) / 1e3
+        print(f"  {n:30s} median {np.median(x):5.2f} p10 {np.percentile(x, 10):5.2f} p90 {np.percentile(x, 90):5.2f} mean {x.mean():5.2f}")
+    x = (d[:, 7] - d[:, 0]) / 1e3
+    print(f"  {'whole tile':30s} median {np.median(x):5.2f} mean {x.mean():5.2f}")
