@@ -344,9 +344,11 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
 #define K1_TRACE(slot) do { if (trace && lane == 0) trace[(uint64_t)(blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
 // phases of the warp's 4th tile (steady state): third region of the trace buffer
 #define K1_TRACE_TILE(slot) do { if (trace && lane == 0 && trace_it == 3u) trace[(uint64_t)(2u * stride + blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
+#define K1_TRACE_TILE2(slot) do { if (trace && lane == 0 && trace_it == 3u) trace[(uint64_t)(3u * stride + blockIdx.x * WARPS + warp) * 8 + (slot)] = globaltimer_ns(); } while (0)
 #else
 #define K1_TRACE(slot) do { } while (0)
 #define K1_TRACE_TILE(slot) do { } while (0)
+#define K1_TRACE_TILE2(slot) do { } while (0)
 #endif
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -519,14 +521,17 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
         uint32_t zw[16], xw[16];                                 // quantized coefficients (zig-zag, int8) / bracket disagreement
         if (TC) {
             if (valid) fence_proxy_async();                      // the luma pass wrote this warp's quarter of A (generic proxy -> MMA)
+            K1_TRACE_TILE2(0);
             tc_fence_before_sync();
             // The tile's four A quarters are in shared memory (and the group's loads of the previous accumulator are
             // done) once all four warps have passed this point.  No warp waits here: each bumps the group's arrival
             // counter (release), and the one that finds the other three already there (acquire) issues the MMA.
             __syncwarp();
+            K1_TRACE_TILE2(1);
             uint32_t arrived = 0;
             if (lane == 0)
                 asm volatile("atom.acq_rel.cta.shared::cta.inc.u32 %0, [%1], 3;" : "=r"(arrived) : "r"(smem_u32(&s_arrive[group])) : "memory");
+            K1_TRACE_TILE2(2);
             if (arrived == 3u) {
                 mbar_wait(table_bar, 0);                       // the limb matrix (immediate after the first tile)
                 tc_fence_after_sync();
@@ -536,6 +541,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                     umma_f16_ss(tmem_d, umma_desc(a_sa + 256u * ks, 128u, 1024u), umma_desc(b_sa + 4096u * ks, 128u, 256u), TC_IDESC, ks > 0 ? 1u : 0u);
                 umma_commit(mma_bar);
             }
+            K1_TRACE_TILE2(3);
             if (valid && s + stride < total) {                   // prefetch: the fence above also covers the reads of the raw tile
                 strip_advance(g, pos, dq, dr);
                 cur = strip_ctx(g, pos);
@@ -577,6 +583,8 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                     uint32_t r[32];
                     JB_TMEM_LD32(tmem_d + tmem_lane + 32u * c, r);
                     tmem_wait_ld();
+                    if (c == 0) K1_TRACE_TILE2(4);
+                    if (c == 1) K1_TRACE_TILE2(5);
 #pragma unroll
                     for (int wi = 0; wi < 4; ++wi) {
                         // columns 8wi..: S0(a) S0(b) S1(a) S1(b) S0(c) S0(d) S1(c) S1(d), (a..d) = zig-zag positions 4w..4w+3
@@ -757,6 +765,7 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
 #endif
 #undef K1_TRACE
 #undef K1_TRACE_TILE
+#undef K1_TRACE_TILE2
     if (flagged_counter) {
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 16);
         nflag += __shfl_xor_sync(0xffffffffu, nflag, 8);

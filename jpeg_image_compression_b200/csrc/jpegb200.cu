@@ -465,8 +465,8 @@ static int launch_block_kernel_t(jpegb200_encoder *enc, cudaStream_t st, const C
     enc->k1_grid = grid;
     enc->k1_warps = Cfg::WARPS;
     if (getenv("JPEGB200_K1_TRACE")) {              // tuning aid: per-warp timestamps
-        if (int rc = enc->trace1.reserve((uint64_t)grid * Cfg::WARPS * 192)) return rc;     // [warps][8] phases, [warps][8] strip ends, [warps][8] phases of the 4th tile
-        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * Cfg::WARPS * 192, st));
+        if (int rc = enc->trace1.reserve((uint64_t)grid * Cfg::WARPS * 256)) return rc;     // [warps][8] phases, [warps][8] strip ends, 2 x [warps][8] phases of the 4th tile
+        JB_CUDA(cudaMemsetAsync(enc->trace1.ptr, 0, (uint64_t)grid * Cfg::WARPS * 256, st));
     }
     {
         TimedLaunch t(enc, st, KID_BLOCK);

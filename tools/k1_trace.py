@@ -22,11 +22,12 @@ grid, wpc = ctypes.c_int(0), ctypes.c_int(0)
 check(enc.lib.jpegb200_encoder_launch_shape(enc.handle, ctypes.byref(grid), ctypes.byref(wpc)), "launch_shape")
 nwarps = grid.value * wpc.value
 print("block kernel grid", grid.value, "x", wpc.value, "warps")
-tr = np.zeros((3 * nwarps, 8), np.uint64)
-check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, 3 * nwarps), "trace")
+tr = np.zeros((4 * nwarps, 8), np.uint64)
+check(enc.lib.jpegb200_encoder_read_k1_trace(enc.handle, tr.ctypes.data, 4 * nwarps), "trace")
 t = tr[:nwarps].astype(np.int64)
 ends = tr[nwarps:2 * nwarps].astype(np.int64)
-detail = tr[2 * nwarps:].astype(np.int64)
+detail = tr[2 * nwarps:3 * nwarps].astype(np.int64)
+detail2 = tr[3 * nwarps:].astype(np.int64)
 t0 = t[:, 0].min()
 names = ["entry", "prologue", "tile0", "-", "-", "-", "exit"]
 print("warps", nwarps, "strips", strips, "span us", (t[:, 6].max() - t0) / 1e3)
@@ -69,3 +70,14 @@ if ok.any():
         print(f"  {n:30s} median {np.median(x):5.2f} p10 {np.percentile(x, 10):5.2f} p90 {np.percentile(x, 90):5.2f} mean {x.mean():5.2f}")
     x = (d[:, 7] - d[:, 0]) / 1e3
     print(f"  {'whole tile':30s} median {np.median(x):5.2f} mean {x.mean():5.2f}")
+
+ok2 = ok & (detail2[:, :6] > 0).all(axis=1)
+if ok2.any():
+    d, e = detail[ok2], detail2[ok2]
+    rows = [("luma done -> proxy fence done", e[:, 0] - d[:, 2]), ("tcgen05 fence + syncwarp", e[:, 1] - e[:, 0]), ("arrival (shared atomic)", e[:, 2] - e[:, 1]),
+            ("MMA issue (last arriver only)", e[:, 3] - e[:, 2]), ("next strip: position + TMA issue", d[:, 3] - e[:, 3]),
+            ("MMA done -> first TMEM chunk loaded", e[:, 4] - d[:, 5]), ("first chunk quantized + second loaded", e[:, 5] - e[:, 4])]
+    print("inside the arrival and quantization phases:")
+    for n, x in rows:
+        x = x / 1e3
+        print(f"  {n:40s} median {np.median(x):5.2f} p10 {np.percentile(x, 10):5.2f} p90 {np.percentile(x, 90):5.2f} mean {x.mean():5.2f}")
