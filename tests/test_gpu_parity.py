@@ -642,3 +642,24 @@ def test_concurrency_hint_does_not_change_bytes(handles):
         b_off = b_off.cpu().numpy()
         assert (a_off[: n + 1] == b_off[: n + 1]).all()
         assert a == b_scan[: int(b_off[n])].cpu().numpy().tobytes()
+
+
+def test_luma_pass_row_alignments(enc, oracle):
+    """K1's lane-per-block luma pass reads 8-byte units: rows whose 16-byte phase is 0 or 8 take it (pitch = 8 mod 16,
+    or a base shifted by 8), every other phase takes the funnel-shift path -- both against the oracle, full strips and
+    a ragged last strip in each row."""
+    import torch
+    rng = np.random.default_rng(77)
+    for (w, h) in [(264, 17), (520, 9), (776, 24), (260, 11), (268, 16), (1032, 8)]:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert enc.encode(rgb) == oracle.encode_scan(rgb), (w, h)
+    w, h = 512, 19
+    rgb = oracle.synth_rgb(w, h, 9, 30)
+    want = oracle.encode_scan(rgb)
+    for shift in (4, 8, 12, 16, 2):
+        buf = torch.zeros(shift + w * h * 3 + 64, dtype=torch.uint8, device="cuda")
+        buf[shift: shift + w * h * 3] = torch.from_numpy(rgb.reshape(-1)).cuda()
+        scan, offs = enc.encode_device(buf[shift:], w, h, 1)
+        enc.status()
+        n = int(offs[1].item())
+        assert scan[:n].cpu().numpy().tobytes() == want, shift
