@@ -663,3 +663,23 @@ def test_luma_pass_row_alignments(enc, oracle):
         enc.status()
         n = int(offs[1].item())
         assert scan[:n].cpu().numpy().tobytes() == want, shift
+
+
+def test_butterfly_transform_mode_equals_default(enc, oracle):
+    """dct_mode 2 (register butterfly transform, kept for comparison) produces the same coefficients and bytes as the
+    tensor-core transform: full strips, ragged strips, a batch, a dense image."""
+    import torch
+    bf = jb.DeviceEncoder(0, dct_mode=2)
+    rng = np.random.default_rng(5)
+    for (w, h) in [(1024, 64), (264, 17), (1001, 77), (16, 9)]:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert bf.encode(rgb) == oracle.encode_scan(rgb), (w, h)
+        assert int((bf.coefficients(_nblocks(rgb)) != oracle.coefficients(rgb)).sum()) == 0, (w, h)
+    d = enc.synth(1920, 1080, 3, 21, 20)
+    a_scan, a_off = enc.encode_device(d, 1920, 1080, 3)
+    b_scan, b_off = bf.encode_device(d, 1920, 1080, 3)
+    torch.cuda.synchronize()
+    n = int(a_off[3].item())
+    assert n == int(b_off[3].item())
+    assert torch.equal(a_scan[:n], b_scan[:n])
+    bf.close()
