@@ -165,6 +165,10 @@ int          jpegb200_encoder_set_dct_mode(jpegb200_encoder *enc, int dct_mode);
  * behind one another's tails: higher aggregate throughput on small images (3840x2160, 8 handles: +18 %), longer
  * latency per image.  Output bytes do not depend on it. */
 int          jpegb200_encoder_set_concurrency(jpegb200_encoder *enc, int handles);
+/* Debugging aid.  With JPEGB200_GUARD=1 in the environment every workspace buffer of a handle is allocated at exactly
+ * the size the launch needs, between two 4 KB guard bands, all filled with 0xA5.  This call synchronises the device and
+ * reports how many guard bytes were overwritten and how many buffers carry guards (0 when the variable is not set). */
+int          jpegb200_encoder_check_guards(jpegb200_encoder *enc, uint64_t *corrupted_bytes, int *guarded_buffers);
 /* Workspace hint: expected packed bytes per 8x8 block, averaged over any 256 consecutive blocks
  * (default 24; up to 32 the entropy kernel runs with its small shared-memory bit windows, above
  * that with the worst-case ones: 184 covers every possible input).  It also sizes the per-image

@@ -69,7 +69,7 @@ EXPORTED_FUNCTIONS = [
     "loadBMPImage", "freeBMPImage", "saveJPEGGrayscale", "freeYImage",
     # fused + device API
     "jpegb200_encode_scan", "jpegb200_encode_scan_dbg", "jpegb200_jfif_header", "jpegb200_device_count",
-    "jpegb200_last_error", "jpegb200_encoder_create", "jpegb200_encoder_destroy", "jpegb200_encoder_set_dct_mode", "jpegb200_encoder_set_concurrency",
+    "jpegb200_last_error", "jpegb200_encoder_create", "jpegb200_encoder_destroy", "jpegb200_encoder_set_dct_mode", "jpegb200_encoder_set_concurrency", "jpegb200_encoder_check_guards",
     "jpegb200_encoder_set_bytes_per_block", "jpegb200_encode_batch_device", "jpegb200_encode_batch_files_device", "jpegb200_encoder_status",
     "jpegb200_encoder_stats", "jpegb200_encoder_read_coefficients", "jpegb200_encoder_read_block_bits", "jpegb200_encoder_read_trace", "jpegb200_encoder_read_k1_trace", "jpegb200_encoder_launch_shape",
     "jpegb200_encoder_set_profiling", "jpegb200_encoder_kernel_times", "jpegb200_encode_host",
@@ -131,6 +131,7 @@ def load_library():
     L.jpegb200_encoder_destroy.restype = None
     L.jpegb200_encoder_set_dct_mode.argtypes = [vp, C.c_int]
     L.jpegb200_encoder_set_concurrency.argtypes = [vp, C.c_int]
+    L.jpegb200_encoder_check_guards.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
     L.jpegb200_encoder_set_bytes_per_block.argtypes = [vp, C.c_int]
     L.jpegb200_encode_batch_device.argtypes = [vp, P(Batch), vp, u64, vp, vp]
     L.jpegb200_encode_batch_files_device.argtypes = [vp, P(Batch), vp, u64, vp, vp]

@@ -169,15 +169,27 @@ static void build_tables(HostTables &t)
 
 // ---- encoder handle ---------------------------------------------------------------
 
+// Workspace buffer.  With JPEGB200_GUARD=1 in the environment (a debugging aid: compute-sanitizer is not available on
+// every box) a buffer is allocated at exactly the requested size between two 4 KB guard bands, everything filled with
+// 0xA5; jpegb200_encoder_check_guards counts the guard bytes that no longer hold the pattern.
+constexpr size_t GUARD_BYTES = 4096;
 struct DeviceBuffer {
     void *ptr = nullptr;
     size_t bytes = 0;
+    void *base = nullptr;            // guard mode: start of the allocation (ptr = base + GUARD_BYTES)
     int reserve(size_t need)
     {
         if (need <= bytes) return JPEGB200_OK;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
+        release();
+        const char *g = getenv("JPEGB200_GUARD");
+        if (g && *g && *g != '0') {
+            const size_t want = (need + 15) & ~(size_t)15;
+            if (!cuda_ok(cudaMalloc(&base, want + 2 * GUARD_BYTES), "cudaMalloc(workspace)")) return JPEGB200_ERR_CUDA;
+            if (!cuda_ok(cudaMemset(base, 0xA5, want + 2 * GUARD_BYTES), "cudaMemset(guard)")) return JPEGB200_ERR_CUDA;
+            ptr = static_cast<uint8_t *>(base) + GUARD_BYTES;
+            bytes = want;
+            return JPEGB200_OK;
+        }
         const size_t want = need + need / 8 + 256;
         if (!cuda_ok(cudaMalloc(&ptr, want), "cudaMalloc(workspace)")) return JPEGB200_ERR_CUDA;
         bytes = want;
@@ -185,9 +197,21 @@ struct DeviceBuffer {
     }
     void release()
     {
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
+        if (base) cudaFree(base);
+        else if (ptr) cudaFree(ptr);
+        ptr = base = nullptr;
         bytes = 0;
+    }
+    // guard mode: number of guard bytes overwritten (-1: CUDA error); 0 for an unguarded buffer
+    long long corrupted() const
+    {
+        if (!base) return 0;
+        std::vector<uint8_t> h(2 * GUARD_BYTES);
+        if (cudaMemcpy(h.data(), base, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (cudaMemcpy(h.data() + GUARD_BYTES, static_cast<uint8_t *>(ptr) + bytes, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        long long bad = 0;
+        for (uint8_t b : h) bad += b != 0xA5;
+        return bad;
     }
 };
 
@@ -647,6 +671,12 @@ extern "C" int jpegb200_device_count(void)
 
 extern "C" const char *jpegb200_last_error(void) { return g_last_error.c_str(); }
 
+static std::vector<jb::DeviceBuffer *> all_buffers(jpegb200_encoder *enc)
+{
+    return {&enc->coef, &enc->blkinfo, &enc->streams, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
+            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace, &enc->trace1};
+}
+
 extern "C" jpegb200_encoder *jpegb200_encoder_create(int device)
 {
     int n = 0;
@@ -677,11 +707,30 @@ extern "C" void jpegb200_encoder_destroy(jpegb200_encoder *enc)
     cudaSetDevice(enc->device);
     cudaDeviceSynchronize();
     harvest_events(enc);
-    for (DeviceBuffer *b : {&enc->coef, &enc->blkinfo, &enc->streams, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
-                            &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace, &enc->trace1})
-        b->release();
+    for (DeviceBuffer *b : all_buffers(enc)) b->release();
     if (enc->pinned_status) cudaFreeHost(enc->pinned_status);
     delete enc;
+}
+
+// Debugging aid (JPEGB200_GUARD=1): guard bytes around the workspace buffers that were overwritten, and how many
+// buffers carry guards.  Synchronises the device.
+extern "C" int jpegb200_encoder_check_guards(jpegb200_encoder *enc, uint64_t *corrupted_bytes, int *guarded_buffers)
+{
+    if (!enc || !corrupted_bytes || !guarded_buffers) return JPEGB200_ERR_ARG;
+    JB_CUDA(cudaSetDevice(enc->device));
+    JB_CUDA(cudaDeviceSynchronize());
+    uint64_t bad = 0;
+    int n = 0;
+    for (jb::DeviceBuffer *b : all_buffers(enc)) {
+        if (!b->base) continue;
+        const long long c = b->corrupted();
+        if (c < 0) return JPEGB200_ERR_CUDA;
+        bad += (uint64_t)c;
+        ++n;
+    }
+    *corrupted_bytes = bad;
+    *guarded_buffers = n;
+    return JPEGB200_OK;
 }
 
 extern "C" int jpegb200_encoder_set_concurrency(jpegb200_encoder *enc, int handles)

@@ -36,6 +36,12 @@ class DeviceEncoder:
         """Launch-shape hint (include/jpegb200.h): `handles` encoders are kept busy side by side on this GPU."""
         check(self.lib.jpegb200_encoder_set_concurrency(self.handle, int(handles)), "set_concurrency")
 
+    def check_guards(self):
+        """(corrupted guard bytes, guarded buffers) -- see JPEGB200_GUARD in include/jpegb200.h."""
+        bad, n = C.c_uint64(0), C.c_int(0)
+        check(self.lib.jpegb200_encoder_check_guards(self.handle, C.byref(bad), C.byref(n)), "check_guards")
+        return int(bad.value), int(n.value)
+
     def close(self):
         if self.handle:
             self.lib.jpegb200_encoder_destroy(self.handle)

@@ -683,3 +683,50 @@ def test_butterfly_transform_mode_equals_default(enc, oracle):
     assert n == int(b_off[3].item())
     assert torch.equal(a_scan[:n], b_scan[:n])
     bf.close()
+
+
+def test_workspace_guard_bands_intact(oracle, monkeypatch):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds WRITES are hunted with guard bands:
+    JPEGB200_GUARD=1 allocates every workspace buffer at exactly the size the launch asks for, between two 4 KB bands
+    of 0xA5 (jpegb200_encoder_check_guards), and the caller-owned output buffers get the same treatment here.  Single
+    images (ragged, tiny, tall, dense with the 184 B/block retry), batch, files mode, stripes, hinted launch shapes."""
+    import torch
+    monkeypatch.setenv("JPEGB200_GUARD", "1")
+    encs = [jb.DeviceEncoder(0) for _ in range(3)]
+    g = encs[0]
+    rng = np.random.default_rng(123)
+    singles = [oracle.synth_rgb(203, 77, 3, 30), oracle.synth_rgb(1, 1, 3, 0), oracle.synth_rgb(2048, 24, 3, 20),
+               oracle.synth_rgb(256, 8 * 8 * 40, 5, 20), rng.integers(0, 256, (48, 264, 3), dtype=np.uint8),
+               oracle.synth_rgb(1001, 333, 4, 64)]
+    for rgb in singles:
+        assert g.encode(rgb) == oracle.encode_scan(rgb), rgb.shape
+    imgs = np.stack([oracle.synth_rgb(120, 50, s, 25) for s in range(5)])
+    for i, s in enumerate(g.encode_batch(imgs)):
+        assert s == oracle.encode_scan(imgs[i]), i
+    hdr = oracle.jfif_header(120, 50)
+    for i, f in enumerate(g.encode_batch_files(imgs)):
+        assert f == hdr + oracle.encode_scan(imgs[i]) + b"\xff\xd9", i
+    # caller-owned device buffers between canaries
+    w, h, n = 640, 101, 3
+    d = g.synth(w, h, n, 5, 20)
+    cap = g.scan_capacity(w, h, n)
+    raw = torch.full((cap + 8192,), 0x5A, dtype=torch.uint8, device="cuda")
+    raw_off = torch.full((n + 1 + 128,), 0x5A5A5A5A, dtype=torch.int64, device="cuda")
+    g.set_concurrency(16)
+    g.encode_device(d, w, h, n, scan=raw[4096: 4096 + cap], offsets=raw_off[64: 64 + n + 1])
+    g.status()
+    g.set_concurrency(1)
+    assert bool((raw[:4096] == 0x5A).all()) and bool((raw[4096 + cap:] == 0x5A).all())
+    assert bool((raw_off[:64] == 0x5A5A5A5A).all()) and bool((raw_off[64 + n + 1:] == 0x5A5A5A5A).all())
+    offs = raw_off[64: 64 + n + 1].cpu().numpy()
+    host = d.cpu().numpy().reshape(n, h, w, 3)
+    for i in range(n):
+        assert raw[4096 + int(offs[i]): 4096 + int(offs[i + 1])].cpu().numpy().tobytes() == oracle.encode_scan(host[i]), i
+    # stripes: three ranks emulated on one GPU
+    rgb = oracle.synth_rgb(300, 203, 3, 25)
+    assert _striped_on_one_gpu(encs, torch.from_numpy(rgb).cuda(), 300, 203) == oracle.encode_scan(rgb)
+    for e in encs:
+        bad, guarded = e.check_guards()
+        assert guarded >= 8, guarded
+        assert bad == 0, bad
+        e.close()
