@@ -8,13 +8,17 @@
 // a strip, one lane a block:
 //   1. TMA into shared memory, mbarrier-completed: for 16-byte aligned inputs ONE tensor-map copy
 //      (cp.async.bulk.tensor.3d / UTMALDG) of the 8 x 768-byte tile, otherwise one bulk copy (UBLKCP) per pixel row;
-//   2. cooperative luma pass: 4 pixels per lane-step (PRMT, DP4A), bytes written to a 256 x 8 Y tile; the next
-//      strip's copy is issued as soon as the raw tile has been read;
+//   2. luma pass, one lane per block: per pixel row three LDS.64 (the block's 8 pixels), eight DP4A whose accumulator
+//      carries the fp16 exponent of 1024, so that one PRMT per pixel pair gives the fp16 pair {1024 + Y} and one HADD2
+//      the level-shifted values; bytes written to a 256 x 8 Y tile, fp16 values (TC) with one STS.128 per row
+//      into the MMA's A operand (ragged or oddly aligned strips: cooperative 4-pixels-per-lane path);
 //   3. transform + quantization, one of
 //      TC = true  (default): the 64-term sums of all 64 coefficients run on the tensor cores.  A tile of 128
 //                 blocks (4 strips = 4 warps) is one tcgen05.mma chain D[128 x 128] = A[128 x 64] * B^T: A = the
-//                 level-shifted luma values as fp16 integers, written by the luma pass straight into the UMMA
-//                 operand layout in shared memory; B = the reference's own LUT products cos[r][u]*cos[c][v] in 22-bit
+//                 level-shifted luma values as fp16 integers in the UMMA operand layout in shared memory; no
+//                 barrier: every warp bumps the group's arrival counter, the last one to arrive issues the MMA,
+//                 and all of them request the next strip's pixels and do the block statistics while it runs;
+//                 B = the reference's own LUT products cos[r][u]*cos[c][v] in 22-bit
 //                 fixed point, split into two 11-bit integer limbs held as fp16 (shared memory, UMMA K-major
 //                 layout).  Every product and partial sum is an integer below 2^24, so the fp32 accumulators in
 //                 TMEM hold the EXACT integer sums; tcgen05.ld hands each lane its block's 128 limb sums, 16
