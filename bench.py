@@ -480,7 +480,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(k1_ms, 5),
                 "kernel_share_of_step": round(k1_ms / step_ms_sum, 3) if step_ms_sum > 0 else None,
                 "per_kernel_ms": {n: round(m / max(c, 1), 5) for n, m, c in zip(kt["names"], kt["ms"], kt["calls"]) if c},
-                "step_frac": round(algo_bytes / (ms_total / timed_steps * 1e-3) / 1e9 / peak, 4)}
+                "step_frac": round(algo_bytes / (ms_total / timed_steps * 1e-3) / 1e9 / peak, 4),
+                # SURVEY.md 8(d) judges the block kernel on its ACTUAL DRAM bytes (ncu) per second; the capture is static
+                "traffic_frac": round(traffic / (k1_ms * 1e-3) / 1e9 / peak, 4) if traffic else None}
 
     # ---- end to end: pinned host buffers -> C-ABI call -> pinned host buffers --------------------
     e2e = None
