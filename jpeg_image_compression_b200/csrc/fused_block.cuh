@@ -2,7 +2,7 @@
 //
 // One pass over the RGB payload: luma (converter.c:51) + edge replication (converter.c:31,36) + level shift
 // (converter.c:84-86) + 8x8 forward DCT (dct.c:63-96) + quantization (quantization.c:34-36) + zig-zag
-// (zigzag.c:51-60).  Output: the quantized coefficients as int8 in zig-zag order, 64 bytes per block.
+// (zigzag.c:51-60).  Output: the quantized coefficients as int8 in zig-zag order, 32 + 32 bytes per block in two planes.
 //
 // Work unit: a STRIP of 32 consecutive 8x8 blocks in one block row (256 x 8 pixels, 6 KB of RGB).  One warp owns
 // a strip, one lane a block:
@@ -27,7 +27,7 @@
 //      TC = false: scaled even/odd butterfly in registers (rows scalar, columns packed fp32), as in round 1.
 //      In both cases the value is bracketed (see below) and the few coefficients whose bracket straddles a rounding
 //      boundary are re-evaluated in the reference's exact operation order;
-//   4. 4 x 128-bit stores of the block's 64 coefficient bytes.
+//   4. 128-bit stores of the block's coefficient bytes: positions 0..31 always, 32..63 only when any is non-zero.
 // The entropy stage is a kernel of its own (strip_entropy.cuh): its sparse symbol walks are latency-bound and want
 // two to three times the occupancy this register-heavy kernel can have (measured: DESIGN.md section 3).
 //
@@ -338,7 +338,7 @@ __host__ __device__ constexpr int gclass(int k) { return (k == 2 || k == 6) ? 1 
 
 template <bool TC>
 __global__ void __launch_bounds__(K1Cfg<TC>::THREADS, K1Cfg<TC>::CTAS_PER_SM)
-k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restrict__ tables, unsigned long long *__restrict__ flagged_counter,
+k_fused_blocks(const Geom g, int8_t *__restrict__ coef, uint32_t *__restrict__ himask, const uint8_t *__restrict__ tables, unsigned long long *__restrict__ flagged_counter,
                const int exact_mode, uint64_t *__restrict__ lookback_state, const uint64_t lookback_words,
                unsigned long long *__restrict__ trace, const __grid_constant__ CUtensorMap tmap_param)
 {
@@ -736,16 +736,29 @@ k_fused_blocks(const Geom g, int8_t *__restrict__ coef, const uint8_t *__restric
                 }
             }
         }
-        if (lane < me.vb) {
-            uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 64);
-#pragma unroll
-#ifdef JB_EXPERIMENT_HALFSTORE
-            for (int i = 0; i < 2; ++i) dst[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
-#elif defined(JB_EXPERIMENT_NOSTORE)
-            if (zw[5] == 0x12345678u) dst[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
-#else
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(zw[4 * i], zw[4 * i + 1], zw[4 * i + 2], zw[4 * i + 3]);
+        // Coefficients 0..31 always (32 bytes per lane, 1 KB per warp, contiguous); 32..63 into their own plane and only
+        // for the blocks that have any (one block in 500 at amp=20, one in four on a busy photograph): the strip's
+        // mask tells the entropy kernel which lanes to read them for.
+        {
+            const uint32_t hi_any = (zw[8] | zw[9] | zw[10] | zw[11] | zw[12] | zw[13] | zw[14] | zw[15]) != 0u && lane < me.vb;
+            const uint32_t mask = __ballot_sync(0xffffffffu, hi_any);
+            if (lane == 0) himask[s] = mask;
+            if (lane < me.vb) {
+                uint4 *dst = reinterpret_cast<uint4 *>(coef + (me.block0 + (uint32_t)lane) * 32);
+#ifdef JB_EXPERIMENT_NOSTORE
+                if (zw[5] == 0x12345678u)
 #endif
+                {
+                    dst[0] = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+                    dst[1] = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+                }
+                if (hi_any) {
+                    // second plane: after the first one's 32 bytes for every block of the launch
+                    uint4 *dsth = reinterpret_cast<uint4 *>(coef + (g.blocks_per_image * (uint64_t)g.count + me.block0 + (uint32_t)lane) * 32);
+                    dsth[0] = make_uint4(zw[8], zw[9], zw[10], zw[11]);
+                    dsth[1] = make_uint4(zw[12], zw[13], zw[14], zw[15]);
+                }
+            }
         }
         __syncwarp();                                            // the Y tile is rewritten by the next strip's luma pass
         K1_TRACE_TILE(7);

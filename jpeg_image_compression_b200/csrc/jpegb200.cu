@@ -224,7 +224,7 @@ struct jpegb200_encoder {
     int concurrency = 1;             // handles the caller keeps busy on this device at the same time (grid sizing)
     int bytes_per_block = 24;
     jb::HostTables tables;
-    jb::DeviceBuffer coef, blkinfo, streams, strips, strip_bits, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace, trace1;
+    jb::DeviceBuffer coef, himask, blkinfo, streams, strips, strip_bits, lookback, image_bits, image_bytes, slots, dtables, misc, host_in, host_scan, trace, trace1;
     uint64_t *pinned_status = nullptr;   // host-pinned {err, pad, offsets[2]}: one D2H + one sync per host call
     uint64_t last_scan_bytes = 0;        // size of the previous host-call result: the speculative D2H length
     uint32_t slot_bytes = 768;      // strip stream slot: 32 blocks x bytes_per_block
@@ -337,7 +337,8 @@ static int prepare(jpegb200_encoder *enc, const uint8_t *d_rgb, int w, int h, in
     enc->slot_bytes = (uint32_t)std::min(32 * enc->bytes_per_block, enc->bytes_per_block <= 32 ? STREAM_SMALL_BYTES : STREAM_BIG_BYTES);
     enc->slot_bytes = (enc->slot_bytes + 15u) & ~15u;
     if ((rc = enc->streams.reserve(g.total_strips * (uint64_t)enc->slot_bytes + 64))) return rc;
-    if ((rc = enc->coef.reserve(tb * 64))) return rc;
+    if ((rc = enc->coef.reserve(tb * 64))) return rc;                 // two planes: positions 0..31, then 32..63 (sparse)
+    if ((rc = enc->himask.reserve(g.total_strips * 4 + 16))) return rc;
     if (enc->want_taps && (rc = enc->blkinfo.reserve(tb * 4))) return rc;
     if ((rc = enc->strips.reserve(g.total_strips * sizeof(StripRec)))) return rc;
     if ((rc = enc->strip_bits.reserve(g.total_strips * 4 + 16))) return rc;
@@ -494,7 +495,7 @@ static int launch_block_kernel_t(jpegb200_encoder *enc, cudaStream_t st, const C
     }
     {
         TimedLaunch t(enc, st, KID_BLOCK);
-        k_fused_blocks<TC><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr), static_cast<const uint8_t *>(enc->dtables.ptr),
+        k_fused_blocks<TC><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, static_cast<int8_t *>(enc->coef.ptr), static_cast<uint32_t *>(enc->himask.ptr), static_cast<const uint8_t *>(enc->dtables.ptr),
                                                                    stats ? misc_flagged(enc) : nullptr, enc->dct_mode == 1 ? 1 : 0,
                                                                    static_cast<uint64_t *>(enc->lookback.ptr), enc->lookback_words,
                                                                    static_cast<unsigned long long *>(enc->trace1.ptr), tmap);
@@ -519,6 +520,8 @@ static int launch_strip_entropy(jpegb200_encoder *enc, cudaStream_t st, bool tap
     const Geom &g = enc->geom;
     StripArgs sa;
     sa.coef = static_cast<const int8_t *>(enc->coef.ptr);
+    sa.coef_hi = sa.coef + enc->total_blocks * 32;
+    sa.himask = static_cast<const uint32_t *>(enc->himask.ptr);
     sa.tables = static_cast<const uint8_t *>(enc->dtables.ptr);
     sa.strips = static_cast<StripRec *>(enc->strips.ptr);
     sa.strip_bits = static_cast<uint32_t *>(enc->strip_bits.ptr);
@@ -673,7 +676,7 @@ extern "C" const char *jpegb200_last_error(void) { return g_last_error.c_str(); 
 
 static std::vector<jb::DeviceBuffer *> all_buffers(jpegb200_encoder *enc)
 {
-    return {&enc->coef, &enc->blkinfo, &enc->streams, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
+    return {&enc->coef, &enc->himask, &enc->blkinfo, &enc->streams, &enc->strips, &enc->strip_bits, &enc->lookback, &enc->image_bits, &enc->image_bytes,
             &enc->slots, &enc->dtables, &enc->misc, &enc->host_in, &enc->host_scan, &enc->trace, &enc->trace1};
 }
 
@@ -839,14 +842,38 @@ extern "C" int jpegb200_encoder_stats(jpegb200_encoder *enc, jpegb200_stats *out
     return JPEGB200_OK;
 }
 
+// Coefficients of blocks [first, first + n) of the last launch as int16 in zig-zag order, assembled from the two planes
+// and the strips' masks (positions 32..63 of a block whose mask bit is clear were not stored: they are zero).
+static int read_block_coefficients(jpegb200_encoder *enc, uint64_t first, uint64_t n, int16_t *host_zz)
+{
+    if (first + n > enc->total_blocks) return JPEGB200_ERR_ARG;
+    const Geom &g = enc->geom;
+    std::vector<int8_t> lo((size_t)n * 32), hi((size_t)n * 32);
+    std::vector<uint32_t> mask((size_t)g.total_strips);
+    const int8_t *base = static_cast<const int8_t *>(enc->coef.ptr);
+    JB_CUDA(cudaMemcpy(lo.data(), base + first * 32, lo.size(), cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpy(hi.data(), base + enc->total_blocks * 32 + first * 32, hi.size(), cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpy(mask.data(), enc->himask.ptr, mask.size() * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t b = first + i, img = b / g.blocks_per_image, rem = b - img * g.blocks_per_image;
+        const uint64_t brow = rem / (uint64_t)g.bw, bx = rem - brow * (uint64_t)g.bw;
+        const uint64_t strip = (img * (uint64_t)g.bh + brow) * (uint64_t)g.spr + bx / 32;
+        const bool has_hi = (mask[strip] >> (bx & 31)) & 1u;
+        for (int k = 0; k < 32; ++k) {
+            host_zz[i * 64 + k] = lo[i * 32 + k];
+            host_zz[i * 64 + 32 + k] = has_hi ? hi[i * 32 + k] : 0;
+        }
+    }
+    return JPEGB200_OK;
+}
+
 extern "C" int jpegb200_encoder_read_coefficients(jpegb200_encoder *enc, int16_t *host_zz, uint64_t nblocks)
 {
     if (!enc || !host_zz || nblocks > enc->total_blocks) return JPEGB200_ERR_ARG;
     JB_CUDA(cudaSetDevice(enc->device));
     JB_CUDA(cudaDeviceSynchronize());
-    std::vector<int8_t> tmp((size_t)nblocks * 64);
-    JB_CUDA(cudaMemcpy(tmp.data(), enc->coef.ptr, tmp.size(), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < tmp.size(); ++i) host_zz[i] = tmp[i];
+    int rc = read_block_coefficients(enc, 0, nblocks, host_zz);
+    if (rc) return rc;
     return JPEGB200_OK;
 }
 
@@ -1160,8 +1187,8 @@ extern "C" JpegEncoderBuffer *jpegb200_encode_scan_dbg(const BMPImage *image, in
         if (host && result) rc = jpegb200_encode_host(enc, image->data, image->width, image->height, host, cap, &n, nullptr);
         if (rc == JPEGB200_OK) {
             if (first_block) {
-                int8_t zz[64];
-                if (cuda_ok(cudaMemcpy(zz, enc->coef.ptr, 64, cudaMemcpyDeviceToHost), "cudaMemcpy(D2H block0)"))
+                int16_t zz[64];
+                if (read_block_coefficients(enc, 0, 1, zz) == JPEGB200_OK)
                     for (int k = 0; k < 64; ++k) first_block[kZigzag[k]] = zz[k];
             }
             result->data = host;

@@ -4,7 +4,8 @@
 // One warp per strip, one lane per 8x8 block, many warps per SM: the symbol walks are sparse, data-dependent and
 // latency-bound, so this kernel is kept light (no transform, few registers) and runs at two to three times the
 // occupancy of the block kernel.
-//   1. the lane's 64 quantized coefficients (int8, zig-zag order: 4 x 128-bit loads, the next strip's are requested
+//   1. the lane's quantized coefficients (int8, zig-zag order: 2 x 128-bit loads for positions 0..31, 2 more only for
+//      the lanes K1 marked as reaching beyond; the next strip's are requested
 //      before this strip is processed) are parked in shared memory and reduced to a 63-bit non-zero map;
 //   2. ONE table walk over the non-zero coefficients: each visit is one look-up of the ready-made symbol word
 //      (code + amplitude bits, length in the low 5 bits); the length is added to the block's bit cost and the word
@@ -222,7 +223,9 @@ __device__ __noinline__ BitWriter emit_tail(BitWriter bw, uint32_t zs, uint32_t 
 
 // geometry + buffers of the strip entropy kernel
 struct StripArgs {
-    const int8_t *coef;            // [blocks][64] zig-zag int8 (K1)
+    const int8_t *coef;            // [blocks][32] zig-zag positions 0..31, int8 (K1)
+    const int8_t *coef_hi;         // [blocks][32] positions 32..63, valid for the lanes in himask[strip]
+    const uint32_t *himask;        // [total_strips]
     const uint8_t *tables;         // device table block
     StripRec *strips;              // [total_strips]
     uint32_t *strip_bits;          // [total_strips] compact copy of StripRec.bits
@@ -306,14 +309,26 @@ k_strip_entropy(const StripArgs a)
     bool first = false;
     uint4 q[4];
     int pred = 0;                                                // lane 0: quantized DC of the block before the strip
+    uint32_t hmask = 0;                                          // lanes of the strip whose positions 32..63 are not all zero
+    auto fetch = [&](uint32_t strip) {                           // the strip's coefficients -> q (positions 32..63 where present)
+        hmask = __ldg(a.himask + strip);
+        if ((uint32_t)lane < vb) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 32);
+            q[0] = src[0];
+            q[1] = src[1];
+            if ((hmask >> lane) & 1u) {
+                const uint4 *srch = reinterpret_cast<const uint4 *>(a.coef_hi + (block0 + lane) * 32);
+                q[2] = srch[0];
+                q[3] = srch[1];
+            } else {
+                q[2] = q[3] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        if (lane == 0 && !first) pred = (int)a.coef[(block0 - 1) * 32];
+    };
     if (s < a.total_strips) {
         locate(block0, vb, first);
-        if ((uint32_t)lane < vb) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 64);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = src[i];
-        }
-        if (lane == 0 && !first) pred = (int)a.coef[(block0 - 1) * 64];
+        fetch(s);
     }
     for (; s < a.total_strips; s += stride) {
         const uint64_t my_block0 = block0;
@@ -324,26 +339,25 @@ k_strip_entropy(const StripArgs a)
         const int prev_strip_dc = pred;
         if ((uint32_t)lane < my_vb) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 zs[4 * i] = q[i].x; zs[4 * i + 1] = q[i].y; zs[4 * i + 2] = q[i].z; zs[4 * i + 3] = q[i].w;
-                const uint32_t m16 = nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) |
-                                     (nonzero_nibble(q[i].w) << 12);
-                if (i < 2) mlo |= m16 << (16 * i);
-                else mhi |= m16 << (16 * (i - 2));
+                mlo |= (nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) | (nonzero_nibble(q[i].w) << 12)) << (16 * i);
             }
             mlo &= ~1u;                                          // position 0 is the DC
             my_dc = (int)(int8_t)(q[0].x & 0xFFu);
+            if (hmask) {                                         // (warp-uniform) some block of the strip reaches beyond position 31
+#pragma unroll
+                for (int i = 2; i < 4; ++i) {
+                    zs[4 * i] = q[i].x; zs[4 * i + 1] = q[i].y; zs[4 * i + 2] = q[i].z; zs[4 * i + 3] = q[i].w;
+                    mhi |= (nonzero_nibble(q[i].x) | (nonzero_nibble(q[i].y) << 4) | (nonzero_nibble(q[i].z) << 8) | (nonzero_nibble(q[i].w) << 12)) << (16 * (i - 2));
+                }
+            }
         }
         // request the next strip's coefficients now: their latency hides behind the walks below
         if (s + stride < a.total_strips) {
             advance();
             locate(block0, vb, first);
-            if ((uint32_t)lane < vb) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(a.coef + (block0 + lane) * 64);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) q[i] = src[i];
-            }
-            if (lane == 0 && !first) pred = (int)a.coef[(block0 - 1) * 64];
+            fetch(s + stride);
         }
         if (!table_ready) {
             mbar_wait(&s_bar, 0);
