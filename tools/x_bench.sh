@@ -1,13 +1,13 @@
 #!/bin/bash
 # Timing experiments on K1 (results are WRONG by construction, only the times mean something; the numbers are in
 # profiles/r02_design_experiments.md section 6): the library built with one of
-#   -DJB_EXPERIMENT_HALFSTORE  half of the coefficient stores     -DJB_EXPERIMENT_NOSTORE  none of them
+#   -DJB_EXPERIMENT_NOSTORE    none of the coefficient stores (the "half of them" variant of section 6 became the two-plane layout)
 #   -DJB_EXPERIMENT_NOFLAG     no exact re-evaluation of flagged coefficients
 # usage:  bash tools/x_bench.sh build     (here: nvcc cross-compiles the variants next to the library)
 #         gpurun -- 'bash tools/x_bench.sh'   (on the B200: batch of 512 x 1080p with each variant, per-kernel times)
 cd "$(dirname "$0")/.."
 P=jpeg_image_compression_b200
-VARIANTS="HALFSTORE NOSTORE NOFLAG"
+VARIANTS="NOSTORE NOFLAG"
 if [ "$1" = "build" ]; then
   make -C $P/csrc all > /dev/null || exit 1
   for v in $VARIANTS; do
