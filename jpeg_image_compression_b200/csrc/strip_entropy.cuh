@@ -407,9 +407,16 @@ k_strip_entropy(const StripArgs a)
             BitWriter bw;
             bw.start(win_sa, incl - my_bits);
 #pragma unroll 1
-            for (uint32_t cp = cache_sa; cp != sw.cend; cp += 128u) {
+            for (uint32_t cp = cache_sa; cp != sw.cend;) {           // two symbols per trip: half the loop and reconvergence overhead
                 const uint32_t e = lds_u32(cp);
+                cp += 128u;
+                const bool more = cp != sw.cend;
+                const uint32_t e2 = more ? lds_u32(cp) : 0u;
                 bw.put(e & ~31u, e & 31u);
+                if (more) {
+                    bw.put(e2 & ~31u, e2 & 31u);
+                    cp += 128u;
+                }
             }
             if (sw.rest_prev >= 0) bw = emit_tail(bw, zs_sa, sw.rest_lo, sw.rest_hi, sw.rest_prev, sym_sa);
             bw.finish();
