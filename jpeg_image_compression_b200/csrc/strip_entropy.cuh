@@ -407,16 +407,17 @@ k_strip_entropy(const StripArgs a)
             BitWriter bw;
             bw.start(win_sa, incl - my_bits);
 #pragma unroll 1
-            for (uint32_t cp = cache_sa; cp != sw.cend;) {           // two symbols per trip: half the loop and reconvergence overhead
-                const uint32_t e = lds_u32(cp);
-                cp += 128u;
-                const bool more = cp != sw.cend;
-                const uint32_t e2 = more ? lds_u32(cp) : 0u;
-                bw.put(e & ~31u, e & 31u);
-                if (more) {
-                    bw.put(e2 & ~31u, e2 & 31u);
-                    cp += 128u;
-                }
+            for (uint32_t cp = cache_sa; cp != sw.cend;) {           // up to four symbols per trip: a quarter of the loop and reconvergence overhead
+                const uint32_t left = (sw.cend - cp) >> 7;
+                const uint32_t e0 = lds_u32(cp);
+                const uint32_t e1 = left > 1u ? lds_u32(cp + 128u) : 0u;
+                const uint32_t e2 = left > 2u ? lds_u32(cp + 256u) : 0u;
+                const uint32_t e3 = left > 3u ? lds_u32(cp + 384u) : 0u;
+                bw.put(e0 & ~31u, e0 & 31u);
+                if (left > 1u) bw.put(e1 & ~31u, e1 & 31u);
+                if (left > 2u) bw.put(e2 & ~31u, e2 & 31u);
+                if (left > 3u) bw.put(e3 & ~31u, e3 & 31u);
+                cp += 128u * min(left, 4u);
             }
             if (sw.rest_prev >= 0) bw = emit_tail(bw, zs_sa, sw.rest_lo, sw.rest_hi, sw.rest_prev, sym_sa);
             bw.finish();
